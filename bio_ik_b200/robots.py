@@ -1,0 +1,156 @@
+"""Hand-authored kinematic tables for the BASELINE.json configurations.
+
+No URDF/SRDF ships with the reference and none exists offline, so
+these are SYNTHETIC look-alikes ("PR2-like", "Shadow-like"): joint order, axes,
+link offsets and limits follow public recollection of pr2_description etc. and
+must not be mistaken for the vendor models.
+"""
+import math
+
+import numpy as np
+
+from ._abi import JOINT_FIXED, JOINT_PRISMATIC, JOINT_REVOLUTE
+from .model import JointModelGroup, Link, RobotModel
+
+PI = math.pi
+
+
+def _arm(side, y):
+    s = side
+    return [
+        Link(f"{s}_shoulder_pan_link", "torso_lift_link", JOINT_REVOLUTE, xyz=(0.0, y, 0.0), axis=(0, 0, 1),
+             lower=(-2.1354 if s == "r" else -0.5646), upper=(0.5646 if s == "r" else 2.1354), velocity=2.088, joint_name=f"{s}_shoulder_pan_joint"),
+        Link(f"{s}_shoulder_lift_link", f"{s}_shoulder_pan_link", JOINT_REVOLUTE, xyz=(0.1, 0, 0), axis=(0, 1, 0), lower=-0.3536, upper=1.2963, velocity=2.082,
+             joint_name=f"{s}_shoulder_lift_joint"),
+        Link(f"{s}_upper_arm_roll_link", f"{s}_shoulder_lift_link", JOINT_REVOLUTE, axis=(1, 0, 0), lower=(-3.75 if s == "r" else -0.65), upper=(0.65 if s == "r" else 3.75),
+             velocity=3.27, joint_name=f"{s}_upper_arm_roll_joint"),
+        Link(f"{s}_upper_arm_link", f"{s}_upper_arm_roll_link", JOINT_FIXED, joint_name=f"{s}_upper_arm_joint"),
+        Link(f"{s}_elbow_flex_link", f"{s}_upper_arm_link", JOINT_REVOLUTE, xyz=(0.4, 0, 0), axis=(0, 1, 0), lower=-2.1213, upper=-0.15, velocity=3.3,
+             joint_name=f"{s}_elbow_flex_joint"),
+        Link(f"{s}_forearm_roll_link", f"{s}_elbow_flex_link", JOINT_REVOLUTE, axis=(1, 0, 0), lower=-PI, upper=PI, bounded=False, velocity=3.6,
+             joint_name=f"{s}_forearm_roll_joint"),
+        Link(f"{s}_forearm_link", f"{s}_forearm_roll_link", JOINT_FIXED, joint_name=f"{s}_forearm_joint"),
+        Link(f"{s}_wrist_flex_link", f"{s}_forearm_link", JOINT_REVOLUTE, xyz=(0.321, 0, 0), axis=(0, 1, 0), lower=-2.0, upper=-0.1, velocity=3.078,
+             joint_name=f"{s}_wrist_flex_joint"),
+        Link(f"{s}_wrist_roll_link", f"{s}_wrist_flex_link", JOINT_REVOLUTE, axis=(1, 0, 0), lower=-PI, upper=PI, bounded=False, velocity=3.6,
+             joint_name=f"{s}_wrist_roll_joint"),
+    ]
+
+
+_ARM_JOINTS = ["shoulder_pan", "shoulder_lift", "upper_arm_roll", "elbow_flex", "forearm_roll", "wrist_flex", "wrist_roll"]
+
+
+def pr2_like():
+    """PR2-like torso + both arms (SURVEY.md §8(d) values).  Groups:
+    right_arm (7 DOF, tip r_wrist_roll_link), left_arm, all (torso + both arms, 15 DOF)."""
+    links = [
+        Link("base_link", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("torso_lift_link", "base_link", JOINT_PRISMATIC, xyz=(-0.05, 0.0, 0.739675), axis=(0, 0, 1), lower=0.0, upper=0.33, velocity=0.013,
+             joint_name="torso_lift_joint"),
+    ] + _arm("r", -0.188) + _arm("l", 0.188)
+    rm = RobotModel("pr2_like", links)
+    groups = {
+        "right_arm": JointModelGroup(rm, "right_arm", [f"r_{j}_joint" for j in _ARM_JOINTS], ["r_wrist_roll_link"]),
+        "left_arm": JointModelGroup(rm, "left_arm", [f"l_{j}_joint" for j in _ARM_JOINTS], ["l_wrist_roll_link"]),
+        "all": JointModelGroup(rm, "all", ["torso_lift_joint"] + [f"r_{j}_joint" for j in _ARM_JOINTS] + [f"l_{j}_joint" for j in _ARM_JOINTS],
+                               ["r_wrist_roll_link", "l_wrist_roll_link"]),
+    }
+    return rm, groups
+
+
+def snake(n=30, link_length=0.1, limit=2.0, velocity=1.0):
+    """n revolute joints with alternating y/z axes, `link_length` m links (cfg4)."""
+    links = [Link("base_link", None, JOINT_FIXED, joint_name="world_joint")]
+    prev = "base_link"
+    for i in range(n):
+        name = f"seg{i}"
+        links.append(Link(name, prev, JOINT_REVOLUTE, xyz=(link_length if i else 0.0, 0, 0), axis=((0, 1, 0) if i % 2 == 0 else (0, 0, 1)), lower=-limit, upper=limit,
+                          velocity=velocity, joint_name=f"j{i}"))
+        prev = name
+    links.append(Link("tip", prev, JOINT_FIXED, xyz=(link_length, 0, 0), joint_name="tip_joint"))
+    rm = RobotModel(f"snake{n}", links)
+    groups = {"all": JointModelGroup(rm, "all", [f"j{i}" for i in range(n)], ["tip"])}
+    return rm, groups
+
+
+def shadow_like_hand():
+    """Shadow-like hand: 2 wrist joints + fingers with (4,4,4,5,5) joints = 24 DOF, 5 fingertips (cfg5)."""
+    links = [
+        Link("forearm", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("wrist", "forearm", JOINT_REVOLUTE, xyz=(0, 0, 0.213), axis=(0, 1, 0), lower=-0.489, upper=0.140, velocity=2.0, joint_name="WRJ2"),
+        Link("palm", "wrist", JOINT_REVOLUTE, xyz=(0, 0, 0.034), axis=(1, 0, 0), lower=-0.698, upper=0.489, velocity=2.0, joint_name="WRJ1"),
+    ]
+    tips, joints = [], ["WRJ2", "WRJ1"]
+
+    def unit(a):
+        a = np.asarray(a, dtype=float)
+        return tuple(a / np.linalg.norm(a))
+
+    def finger(prefix, base_xyz, specs, base_rpy=(0, 0, 0)):
+        prev = "palm"
+        n = len(specs)
+        for k, (xyz, axis, lo, hi) in enumerate(specs):
+            name, jn = f"{prefix}{k}", f"{prefix.upper()}J{n - k}"
+            links.append(Link(name, prev, JOINT_REVOLUTE, xyz=(base_xyz if k == 0 else xyz), rpy=(base_rpy if k == 0 else (0, 0, 0)), axis=unit(axis), lower=lo, upper=hi,
+                              velocity=2.0, joint_name=jn))
+            joints.append(jn)
+            prev = name
+        links.append(Link(f"{prefix}tip", prev, JOINT_FIXED, xyz=(0, 0, 0.026), joint_name=f"{prefix}tip_joint"))
+        tips.append(f"{prefix}tip")
+
+    f4 = [((0, 0, 0), (0, -1, 0), -0.349, 0.349), ((0, 0, 0), (1, 0, 0), 0.0, 1.571), ((0, 0, 0.045), (1, 0, 0), 0.0, 1.571), ((0, 0, 0.025), (1, 0, 0), 0.0, 1.571)]
+    lf = [((0, 0, 0), (0.571, 0, 0.821), 0.0, 0.785), ((0, 0, 0.066), (0, -1, 0), -0.349, 0.349)] + f4[1:]
+    th = [((0, 0, 0), (0, 0, -1), -1.047, 1.047), ((0, 0, 0), (1, 0, 0), 0.0, 1.222), ((0, 0, 0.038), (1, 0, 0), -0.209, 0.209), ((0, 0, 0), (0, -1, 0), -0.698, 0.698),
+          ((0, 0, 0.032), (0, -1, 0), 0.0, 1.571)]
+    finger("ff", (0.033, 0, 0.095), f4)
+    finger("mf", (0.011, 0, 0.099), f4)
+    finger("rf", (-0.011, 0, 0.095), f4)
+    finger("lf", (-0.033, 0, 0.0207), lf)
+    finger("th", (0.034, -0.0085, 0.029), th, base_rpy=(0, 0.785, 0))
+    rm = RobotModel("shadow_like_hand", links)
+    groups = {"hand": JointModelGroup(rm, "hand", joints, tips)}
+    return rm, groups
+
+
+def random_tree(seed=0, n_joints=9, branch_at=4, prismatic_every=4):
+    """Randomised two-tip tree with rotated joint origins and mixed revolute /
+    prismatic / fixed joints: a test robot that exercises every quaternion path."""
+    rng = np.random.default_rng(seed)
+    links = [Link("root", None, JOINT_FIXED, xyz=rng.uniform(-0.1, 0.1, 3), rpy=rng.uniform(-1, 1, 3), joint_name="root_joint")]
+    names = ["root"]
+    joints = []
+
+    def add(parent, name):
+        k = len(links)
+        if k % 5 == 3:
+            jt = JOINT_FIXED
+        elif k % prismatic_every == 2:
+            jt = JOINT_PRISMATIC
+        else:
+            jt = JOINT_REVOLUTE
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        if jt == JOINT_PRISMATIC:
+            lo, hi = -0.2, 0.3
+        else:
+            lo, hi = sorted(rng.uniform(-2.5, 2.5, 2))
+            if hi - lo < 0.5:
+                hi = lo + 0.5
+        continuous = jt == JOINT_REVOLUTE and k % 7 == 6
+        links.append(Link(name, parent, jt, xyz=rng.uniform(-0.3, 0.3, 3), rpy=rng.uniform(-PI, PI, 3), axis=ax, lower=(-PI if continuous else lo), upper=(PI if continuous else hi),
+                          bounded=not continuous, velocity=float(rng.uniform(0.5, 4.0)), joint_name=name + "_joint"))
+        if jt != JOINT_FIXED:
+            joints.append(name + "_joint")
+        return name
+
+    prev = "root"
+    trunk = []
+    for i in range(n_joints):
+        prev = add(prev, f"a{i}")
+        trunk.append(prev)
+    prev = trunk[branch_at]
+    for i in range(3):
+        prev = add(prev, f"b{i}")
+    rm = RobotModel(f"random_tree{seed}", links)
+    groups = {"all": JointModelGroup(rm, "all", joints, [trunk[-1], prev])}
+    return rm, groups

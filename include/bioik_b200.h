@@ -1,0 +1,217 @@
+/*
+ * bioik_b200.h — C ABI of libbioik_b200.so: the B200-native bio2 / bio2_memetic
+ * population loop of TAMS-Group/bio_ik, evaluated for whole batches of
+ * independent IK queries on one GPU.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree).
+ * Plain pointers and sizes only; no C++/torch/CUDA types cross this header.
+ * All functions return a BIOIK_* status and never throw across the ABI;
+ * bioik_last_error() returns a human-readable message for the last failure.
+ *
+ * There is NO CPU fallback behind this ABI: every compute entry point launches
+ * sm_100a kernels and fails with BIOIK_E_CUDA if no usable device is present.
+ */
+#ifndef BIOIK_B200_H
+#define BIOIK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIOIK_ABI_VERSION 1
+
+/* ---- status codes (reference: ERROR(...) -> std::runtime_error, src/utils.h:122-129) */
+enum {
+    BIOIK_OK = 0,
+    BIOIK_E_INVALID = 1,          /* bad argument / inconsistent tables            */
+    BIOIK_E_UNSUPPORTED_GOAL = 2, /* goal needs a host callback / FCL (JointFunction,
+                                     LinkFunction, Touch): keep the stock CPU solver */
+    BIOIK_E_UNSUPPORTED_JOINT = 3,
+    BIOIK_E_CUDA = 4,             /* CUDA runtime error or no device                */
+    BIOIK_E_NO_PROBLEM = 5,       /* solve called before bioik_set_problem          */
+    BIOIK_E_LIMIT = 6             /* problem exceeds a compiled-in capacity         */
+};
+
+/* ---- joint types (moveit::core::JointModel::JointType as used by
+ *      src/forward_kinematics.h:78-139) */
+enum {
+    BIOIK_JOINT_FIXED = 0,
+    BIOIK_JOINT_REVOLUTE = 1,
+    BIOIK_JOINT_PRISMATIC = 2,
+    BIOIK_JOINT_FLOATING = 3, /* 7 variables: x y z qx qy qz qw */
+    BIOIK_JOINT_PLANAR = 4    /* 3 variables: x y theta         */
+};
+
+/* ---- goal types: the closed-form goal classes of include/bio_ik/goal_types.h.
+ *      p[] layout per type is given beside each enumerator.  Quaternions are
+ *      (x,y,z,w) and must already be normalised the way the reference
+ *      constructors/setters do it (goal_types.h:110,114,139,146). */
+enum {
+    BIOIK_GOAL_POSITION = 1,             /* goal_types.h:96      p[0..2]=position                       */
+    BIOIK_GOAL_ORIENTATION = 2,          /* goal_types.h:115-119 p[3..6]=orientation                    */
+    BIOIK_GOAL_POSE = 3,                 /* goal_types.h:149-180 p[0..2],p[3..6],p[7]=rotation_scale    */
+    BIOIK_GOAL_LOOK_AT = 4,              /* goal_types.h:204-211 p[0..2]=axis p[3..5]=target            */
+    BIOIK_GOAL_MAX_DISTANCE = 5,         /* goal_types.h:235-240 p[0..2]=target p[3]=distance           */
+    BIOIK_GOAL_MIN_DISTANCE = 6,         /* goal_types.h:264-269 p[0..2]=target p[3]=distance           */
+    BIOIK_GOAL_LINE = 7,                 /* goal_types.h:293-297 p[0..2]=position p[3..5]=direction     */
+    BIOIK_GOAL_PLANE = 8,                /* goal_types.h:321-327 p[0..2]=position p[3..5]=normal        */
+    BIOIK_GOAL_AVOID_JOINT_LIMITS = 9,   /* goal_types.h:387-401 (no params)                            */
+    BIOIK_GOAL_CENTER_JOINTS = 10,       /* goal_types.h:412-425 (no params)                            */
+    BIOIK_GOAL_REGULARIZATION = 11,      /* goal_types.h:435-444 (no params)                            */
+    BIOIK_GOAL_MINIMAL_DISPLACEMENT = 12,/* goal_types.h:455-465 (no params)                            */
+    BIOIK_GOAL_JOINT_VARIABLE = 13,      /* goal_types.h:494-498 var=robot variable, p[0]=position      */
+    BIOIK_GOAL_SIDE = 14,                /* goal_types.h:606-613 p[0..2]=axis p[3..5]=direction         */
+    BIOIK_GOAL_DIRECTION = 15            /* goal_types.h:637-643 p[0..2]=axis p[3..5]=direction         */
+};
+
+#define BIOIK_GOAL_NPARAM 12
+
+/* Flattened moveit::core::RobotModel.  One parent joint
+ * per link; joint arrays are indexed by the joint's child link.  Links must be
+ * ordered parents-before-children.  Replaces what RobotJointEvaluator /
+ * RobotFK_Fast_Base / RobotInfo read from MoveIt
+ * (src/forward_kinematics.h:192-213,230-246; include/bio_ik/robot_info.h:70-105). */
+typedef struct BioikRobot {
+    int32_t n_links;
+    int32_t n_vars;
+    const int32_t* link_parent;      /* [n_links] parent link, -1 for the root                      */
+    const int32_t* joint_type;       /* [n_links] BIOIK_JOINT_*                                     */
+    const int32_t* joint_first_var;  /* [n_links] first variable index (-1 if the joint has none)   */
+    const double* link_origin;       /* [n_links][7] getJointOriginTransform(): px py pz qx qy qz qw */
+    const double* joint_axis;        /* [n_links][3] revolute / prismatic axis                      */
+    const int32_t* joint_mimic;      /* [n_links] child link of the mimicked joint, -1 if none      */
+    const double* joint_mimic_factor;/* [n_links]                                                   */
+    const double* joint_mimic_offset;/* [n_links]                                                   */
+    const double* var_min;           /* [n_vars] VariableBounds::min_position_                      */
+    const double* var_max;           /* [n_vars] VariableBounds::max_position_                      */
+    const int32_t* var_bounded;      /* [n_vars] VariableBounds::position_bounded_                  */
+    const double* var_max_velocity;  /* [n_vars] VariableBounds::max_velocity_                      */
+} BioikRobot;
+
+/* Flattened GoalInfo (src/problem.h:121-130; field set of the older struct at
+ * src/problem.h:91-117). */
+typedef struct BioikGoal {
+    int32_t type;      /* BIOIK_GOAL_*                                                          */
+    int32_t tip;       /* index into BioikProblem::tip_links (link goals), else 0               */
+    int32_t secondary; /* GoalContext::goal_secondary_                                          */
+    int32_t var;       /* JOINT_VARIABLE: robot variable index                                  */
+    double weight;     /* GoalContext::goal_weight_  (fitness uses weight*weight)               */
+    double p[BIOIK_GOAL_NPARAM]; /* default parameters; per-query values override them in solve */
+} BioikGoal;
+
+/* Flattened Problem (src/problem.h:131-136, built by src/problem.cpp:72-228). */
+typedef struct BioikProblem {
+    int32_t n_tips;
+    const int32_t* tip_links;   /* [n_tips] Problem::tip_link_indices                      */
+    int32_t n_active;
+    const int32_t* active_vars; /* [n_active] Problem::active_variables (gene order)       */
+    int32_t n_goals;
+    const BioikGoal* goals;     /* primary and secondary goals in Problem order            */
+    double dpos, drot, dtwist;  /* IKParams thresholds, src/problem.cpp:90-95 (DBL_MAX=off) */
+} BioikProblem;
+
+/* Solver constants the reference hard-codes (src/ik_evolution_2.cpp:137-138,
+ * 349-351,453) exposed as parameters. */
+typedef struct BioikSolverCfg {
+    int32_t population;    /* children.size() = 2 parents + child_count; reference 18   */
+    int32_t generations;   /* per species per step(): reference 8 (memetic) / 16        */
+    int32_t memetic;       /* 0 = bio2, 'q' = bio2_memetic, 'l' = bio2_memetic_l        */
+    int32_t memetic_iters; /* reference 8                                               */
+    uint32_t table_seed;   /* IKParams::random_seed: seeds the two shared 8Mi lookup
+                              tables exactly like Random::Random (src/ik_base.h:118-125) */
+    int32_t device;        /* CUDA device ordinal                                       */
+} BioikSolverCfg;
+
+typedef struct bioik_ctx bioik_ctx;
+
+/* IKFactory::create(name, params) + IKBase ctor (src/ik_parallel.h:119,
+ * src/ik_base.h:144-151): builds the solver context, uploads the robot table and
+ * the two RNG lookup tables to HBM. */
+int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx** out);
+void bioik_destroy(bioik_ctx* ctx);
+
+/* IKBase::initialize(problem) + IKEvolution2::initialize structure part
+ * (src/ik_base.h:154-161, src/ik_evolution_2.cpp:111-230): link schedule, gene
+ * limits, goal table.  Per-query data (targets, seeds) arrive with solve. */
+int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem);
+
+/* The batch form of IKParallel::solve -> solverthread (src/ik_parallel.h:148-269)
+ * around IKEvolution2::step (src/ik_evolution_2.cpp:328-646) with the timeout
+ * replaced by a step budget (SURVEY.md §8(c) batch contract):
+ *   query q starts as a freshly constructed solver sharing the lookup tables,
+ *   rng = minstd_rand(rng_seeds[q]), runs `steps` step()s; success is tested on
+ *   getSolution() after steps 1,5,9,... and after the last step; with
+ *   early_exit != 0 a query stops at its first successful test, like the
+ *   reference driver.
+ * Host pointers; H2D/D2H copies are part of the call.
+ *   goal_params   [B][n_goals][BIOIK_GOAL_NPARAM] or NULL (use BioikGoal::p)
+ *   seeds         [B][n_vars]  Problem::initial_guess (full variable vector)
+ *   rng_seeds     [B]
+ *   out_solutions [B][n_vars]  IKSolver::getSolution()
+ *   out_fitness   [B]          primary fitness of the solution (ik_parallel.h:181)
+ *   out_success   [B]          Problem::checkSolutionActiveVariables of the solution
+ *   out_steps     [B]          step() calls executed for the query                   */
+int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, const double* seeds,
+                      const uint32_t* rng_seeds, int32_t steps, int32_t early_exit,
+                      double* out_solutions, double* out_fitness, int32_t* out_success,
+                      int32_t* out_steps);
+
+/* Same, all buffers already resident in device memory of ctx's device; work is
+ * enqueued on `cuda_stream` (a cudaStream_t passed as void*, NULL = the context's
+ * own stream) and NOT synchronised. */
+int bioik_solve_batch_device(bioik_ctx* ctx, int32_t B, const double* d_goal_params,
+                             const double* d_seeds, const uint32_t* d_rng_seeds, int32_t steps,
+                             int32_t early_exit, double* d_out_solutions, double* d_out_fitness,
+                             int32_t* d_out_success, int32_t* d_out_steps, void* cuda_stream);
+
+/* Block until the context's stream has drained. */
+int bioik_synchronize(bioik_ctx* ctx);
+
+/* ---- component entry points (used by the parity tests; same kernels) -------- */
+
+/* RobotFK_Fast_Base::applyConfiguration (src/forward_kinematics.h:331-354) for a
+ * batch of full variable vectors [B][n_vars] -> tip frames [B][n_tips][7]. */
+int bioik_fk_batch(bioik_ctx* ctx, int32_t B, const double* variables, double* out_tip_frames);
+
+/* RobotFK_Jacobian::computeJacobian + RobotFK_Mutator::initializeMutationApproximator
+ * (src/forward_kinematics.h:600-730,802-930) at [B][n_vars] base points ->
+ * delta frames [B][n_tips][n_active][7] (pos xyz, rot xyzw). */
+int bioik_approx_batch(bioik_ctx* ctx, int32_t B, const double* variables, double* out_delta_frames);
+
+/* computeApproximateMutations + computeFitnessActiveVariables
+ * (src/forward_kinematics.h:1061-1233, src/ik_base.h:167-185) at base points
+ * [B][n_vars] for genotypes [B][M][n_active] -> primary and secondary fitness
+ * [B][M] each (either output may be NULL). */
+int bioik_approx_fitness_batch(bioik_ctx* ctx, int32_t B, int32_t M, const double* goal_params,
+                               const double* seeds, const double* base_variables,
+                               const double* genotypes, double* out_primary, double* out_secondary);
+
+/* Solver state after `steps` steps, for trajectory-level parity:
+ *   out_genes     [B][2 species][2 individuals][n_active]
+ *   out_gradients [B][2][2][n_active]
+ *   out_species_fitness [B][2]   (array order, i.e. after the species sort)     */
+int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params,
+                            const double* seeds, const uint32_t* rng_seeds, int32_t steps,
+                            double* out_genes, double* out_gradients,
+                            double* out_species_fitness, double* out_solutions,
+                            double* out_fitness);
+
+/* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
+int64_t bioik_launch_count(const bioik_ctx* ctx);
+
+/* Device-time of the dominant (generation) kernel accumulated since the last call
+ * with reset != 0, measured with CUDA events on the launching stream; returns
+ * milliseconds and the number of launches through the out parameters. */
+int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int64_t* out_launches_evolve,
+                      double* out_ms_serial, int64_t* out_launches_serial);
+
+const char* bioik_last_error(const bioik_ctx* ctx); /* ctx may be NULL: create() errors */
+int bioik_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOIK_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle_strict.so) — test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from bio_ik_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+
+
+class Oracle:
+    def __init__(self, variant="strict"):
+        path = os.path.join(ORACLE_DIR, f"liboracle_{variant}.so")
+        if not os.path.exists(path):
+            build_oracle()
+        self.lib = lib = C.CDLL(path)
+        dp, ip, up = _abi.c_double_p, _abi.c_int32_p, _abi.c_uint32_p
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_tables_create.argtypes = [C.c_uint32]
+        lib.oracle_tables_create.restype = C.c_void_p
+        lib.oracle_tables_destroy.argtypes = [C.c_void_p]
+        lib.oracle_tables_uniform.argtypes = [C.c_void_p]
+        lib.oracle_tables_uniform.restype = dp
+        lib.oracle_tables_gauss.argtypes = [C.c_void_p]
+        lib.oracle_tables_gauss.restype = dp
+        lib.oracle_xorshift.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
+        lib.oracle_minstd_uniform.argtypes = [C.c_uint32, C.c_int, dp]
+        lib.oracle_minstd_normal.argtypes = [C.c_uint32, C.c_int, dp]
+        lib.oracle_minstd_index.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+        lib.oracle_sincos.argtypes = [C.c_int, dp, dp, dp]
+        lib.oracle_concat.argtypes = [dp, dp, dp]
+        lib.oracle_invert.argtypes = [dp, dp]
+        lib.oracle_change.argtypes = [dp, dp, dp, dp]
+        lib.oracle_fk_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp]
+        lib.oracle_approx_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, dp, dp, ip, dp]
+        lib.oracle_approx_fitness_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
+        lib.oracle_solve_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_void_p, C.c_int, dp, dp, up,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp]
+        lib.oracle_hardware_threads.restype = C.c_int
+        self._tables = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.lib.oracle_last_error().decode())
+
+    def tables(self, seed):
+        if seed not in self._tables:
+            self._tables[seed] = self.lib.oracle_tables_create(seed)
+        return self._tables[seed]
+
+    def table_arrays(self, seed, n=None):
+        t = self.tables(seed)
+        n = n or (1 << 23)
+        u = np.ctypeslib.as_array(self.lib.oracle_tables_uniform(t), shape=(1 << 23,))[:n]
+        g = np.ctypeslib.as_array(self.lib.oracle_tables_gauss(t), shape=(1 << 23,))[:n]
+        return u, g
+
+    def sincos(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        s, c = np.empty_like(x), np.empty_like(x)
+        self.lib.oracle_sincos(len(x), _abi.dptr(x), _abi.dptr(s), _abi.dptr(c))
+        return s, c
+
+    def fk(self, robot, problem, variables, libm=False, links=False):
+        v = np.ascontiguousarray(variables, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, T = v.shape[0], len(problem.tip_link_indices)
+        out = np.zeros((B, T, 7))
+        lf = np.zeros((B, len(robot.links), 7)) if links else None
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.oracle_fk_batch(C.byref(r), C.byref(p), int(libm), B, _abi.dptr(v), _abi.dptr(out), _abi.dptr(lf)))
+        return (out, lf) if links else out
+
+    def approx(self, robot, problem, variables, jacobian=False):
+        v = np.ascontiguousarray(variables, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, T, n = v.shape[0], len(problem.tip_link_indices), len(problem.active_variables)
+        delta = np.zeros((B, T, n, 7))
+        mask = np.zeros((B, T, n), dtype=np.int32)
+        jac = np.zeros((B, 6 * T, n))
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.oracle_approx_batch(C.byref(r), C.byref(p), B, _abi.dptr(v), _abi.dptr(delta), _abi.iptr(mask), _abi.dptr(jac)))
+        return (delta, mask, jac) if jacobian else (delta, mask)
+
+    def approx_fitness(self, robot, problem, goal_params, seeds, base, genotypes):
+        base = np.ascontiguousarray(base, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, n = base.shape[0], len(problem.active_variables)
+        g = np.ascontiguousarray(genotypes, dtype=np.float64).reshape(B, -1, n)
+        M = g.shape[1]
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(B, robot.n_vars)
+        gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
+        prim, sec = np.zeros((B, M)), np.zeros((B, M))
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.oracle_approx_fitness_batch(C.byref(r), C.byref(p), B, M, _abi.dptr(gp), _abi.dptr(seeds), _abi.dptr(base), _abi.dptr(g), _abi.dptr(prim), _abi.dptr(sec)))
+        return prim, sec
+
+    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, flags=0, nthreads=0, table_seed=None):
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, n = seeds.shape[0], len(problem.active_variables)
+        gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
+        rs = np.ascontiguousarray(rng_seeds, dtype=np.uint32)
+        res = dict(solutions=np.zeros((B, robot.n_vars)), fitness=np.zeros(B), success=np.zeros(B, dtype=np.int32), steps=np.zeros(B, dtype=np.int32),
+                   genes=np.zeros((B, 2, 2, n)), gradients=np.zeros((B, 2, 2, n)), species_fitness=np.zeros((B, 2)))
+        r, p = robot.to_abi(), problem.to_abi()
+        t = self.tables(cfg.table_seed if table_seed is None else table_seed)
+        nthreads = nthreads or min(B, os.cpu_count() or 1)
+        self._check(self.lib.oracle_solve_batch(C.byref(r), C.byref(p), C.byref(cfg), t, B, _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit), flags, nthreads,
+                                                _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["steps"]),
+                                                _abi.dptr(res["genes"]), _abi.dptr(res["gradients"]), _abi.dptr(res["species_fitness"])))
+        return res
+
+
+def make_cfg(population=18, generations=8, memetic="q", memetic_iters=8, table_seed=1, device=0):
+    c = _abi.BioikSolverCfg()
+    c.population, c.generations = population, generations
+    c.memetic = ord(memetic) if isinstance(memetic, str) and memetic else int(memetic or 0)
+    c.memetic_iters, c.table_seed, c.device = memetic_iters, table_seed, device
+    return c
