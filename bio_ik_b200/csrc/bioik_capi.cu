@@ -1,0 +1,555 @@
+// bioik_capi.cu — host side of libbioik_b200.so: the C ABI of include/bioik_b200.h.
+// Flattens the robot/problem tables (the host-side halves of IKBase::initialize /
+// RobotFK_Fast_Base::initialize / RobotFK_Jacobian::initialize), generates the reference's
+// RNG lookup tables, owns device memory and the stream, and launches the kernels of
+// bioik_kernels.cuh.  No CPU compute path exists here: every solve runs on the GPU.
+#include "../../include/bioik_b200.h"
+#include "bioik_host.hpp"
+#include "bioik_kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace bioik;
+
+namespace
+{
+thread_local std::string g_create_error;
+
+struct EventPair
+{
+    cudaEvent_t a, b;
+    int kind; // 0 = evolve, 1 = serial
+};
+} // namespace
+
+struct bioik_ctx
+{
+    BioikSolverCfg cfg;
+    HostRobot robot;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int64_t launches = 0;
+
+    bool has_problem = false;
+    DProblem hP;
+    DProblem* dP = nullptr;
+
+    double *d_uniform = nullptr, *d_gauss = nullptr;
+
+    // schedules (depend on steps, gens, C, n)
+    int sched_steps = -1, sched_n = -1;
+    int32_t* d_gauss_off = nullptr;
+    uint8_t* d_rate_exp = nullptr;
+
+    // state
+    int capB = 0;
+    DState S;
+    void* state_block = nullptr;
+    // staging for the host-pointer API
+    int stageB = 0;
+    double *d_gp = nullptr, *d_seeds = nullptr, *d_osol = nullptr, *d_ofit = nullptr;
+    uint32_t* d_rs = nullptr;
+    int32_t *d_osucc = nullptr, *d_osteps = nullptr;
+    double* d_default_gp = nullptr; // [G][NPARAM] defaults (goal_params == NULL)
+
+    // timing
+    std::vector<EventPair> pending, pool;
+    double ms_evolve = 0, ms_serial = 0;
+    int64_t n_evolve = 0, n_serial = 0;
+};
+
+namespace
+{
+#define CU(ctx, call)                                                                                             \
+    do                                                                                                            \
+    {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                  \
+        if(e_ != cudaSuccess)                                                                                     \
+        {                                                                                                         \
+            (ctx)->error = std::string(#call) + ": " + cudaGetErrorString(e_);                                    \
+            return BIOIK_E_CUDA;                                                                                  \
+        }                                                                                                         \
+    } while(0)
+
+int fail(bioik_ctx* ctx, int code, const std::string& msg)
+{
+    if(ctx)
+        ctx->error = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int ensure_state(bioik_ctx* ctx, int B)
+{
+    if(B <= ctx->capB) return BIOIK_OK;
+    if(ctx->state_block) cudaFree(ctx->state_block);
+    ctx->state_block = nullptr;
+    const DProblem& P = ctx->hP;
+    size_t n = P.n, T = P.T, gens = ctx->cfg.generations;
+    size_t sizes[] = {
+        (size_t)B * 4 * n * 8,         // genes
+        (size_t)B * 4 * n * 8,         // grads
+        (size_t)B * 2 * 8,             // sfit
+        (size_t)B * 2 * 4,             // impr
+        (size_t)B * n * 8,             // sol
+        (size_t)B * 8,                 // solfit
+        (size_t)B * 4,                 // rng
+        (size_t)B * 4,                 // done
+        (size_t)B * 4,                 // steps
+        (size_t)B * 4,                 // success
+        (size_t)B * 2 * gens * 4,      // ccount
+        (size_t)B * 2 * n * 8,         // base
+        (size_t)B * 2 * T * 7 * 8,     // tip0
+        (size_t)B * 2 * T * n * 7 * 8, // delta
+    };
+    size_t total = 0;
+    for(size_t s : sizes) total += align_up(s);
+    CU(ctx, cudaMalloc(&ctx->state_block, total));
+    char* p = (char*)ctx->state_block;
+    auto take = [&](size_t s) {
+        char* r = p;
+        p += align_up(s);
+        return r;
+    };
+    DState& S = ctx->S;
+    S.genes = (double*)take(sizes[0]);
+    S.grads = (double*)take(sizes[1]);
+    S.sfit = (double*)take(sizes[2]);
+    S.impr = (int32_t*)take(sizes[3]);
+    S.sol = (double*)take(sizes[4]);
+    S.solfit = (double*)take(sizes[5]);
+    S.rng = (uint32_t*)take(sizes[6]);
+    S.done = (int32_t*)take(sizes[7]);
+    S.steps = (int32_t*)take(sizes[8]);
+    S.success = (int32_t*)take(sizes[9]);
+    S.ccount = (int32_t*)take(sizes[10]);
+    S.base = (double*)take(sizes[11]);
+    S.tip0 = (double*)take(sizes[12]);
+    S.delta = (double*)take(sizes[13]);
+    ctx->capB = B;
+    return BIOIK_OK;
+}
+
+int ensure_staging(bioik_ctx* ctx, int B)
+{
+    if(B <= ctx->stageB) return BIOIK_OK;
+    cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps);
+    ctx->stageB = 0;
+    const DProblem& P = ctx->hP;
+    CU(ctx, cudaMalloc(&ctx->d_gp, (size_t)B * P.G * GOAL_NPARAM * 8));
+    CU(ctx, cudaMalloc(&ctx->d_seeds, (size_t)B * P.n_vars * 8));
+    CU(ctx, cudaMalloc(&ctx->d_rs, (size_t)B * 4));
+    CU(ctx, cudaMalloc(&ctx->d_osol, (size_t)B * P.n_vars * 8));
+    CU(ctx, cudaMalloc(&ctx->d_ofit, (size_t)B * 8));
+    CU(ctx, cudaMalloc(&ctx->d_osucc, (size_t)B * 4));
+    CU(ctx, cudaMalloc(&ctx->d_osteps, (size_t)B * 4));
+    ctx->stageB = B;
+    return BIOIK_OK;
+}
+
+int ensure_schedules(bioik_ctx* ctx, int steps)
+{
+    if(ctx->sched_steps >= steps && ctx->sched_n == ctx->hP.n) return BIOIK_OK;
+    std::vector<int32_t> go;
+    std::vector<uint8_t> re;
+    make_schedules(steps, ctx->cfg.generations, ctx->cfg.population, ctx->hP.n, go, re);
+    cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp);
+    ctx->d_gauss_off = nullptr, ctx->d_rate_exp = nullptr;
+    CU(ctx, cudaMalloc(&ctx->d_gauss_off, go.size() * 4));
+    CU(ctx, cudaMalloc(&ctx->d_rate_exp, re.size()));
+    CU(ctx, cudaMemcpy(ctx->d_gauss_off, go.data(), go.size() * 4, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_rate_exp, re.data(), re.size(), cudaMemcpyHostToDevice));
+    ctx->sched_steps = steps;
+    ctx->sched_n = ctx->hP.n;
+    return BIOIK_OK;
+}
+
+EventPair get_pair(bioik_ctx* ctx, int kind)
+{
+    EventPair p;
+    if(!ctx->pool.empty())
+    {
+        p = ctx->pool.back();
+        ctx->pool.pop_back();
+    }
+    else
+    {
+        cudaEventCreate(&p.a);
+        cudaEventCreate(&p.b);
+    }
+    p.kind = kind;
+    return p;
+}
+
+void drain_events(bioik_ctx* ctx);
+
+int check_launch(bioik_ctx* ctx, const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if(e != cudaSuccess)
+    {
+        ctx->error = std::string(what) + ": " + cudaGetErrorString(e);
+        return BIOIK_E_CUDA;
+    }
+    ctx->launches++;
+    return BIOIK_OK;
+}
+
+// enqueue a whole solve on `st`; all pointers are device pointers
+int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
+{
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    if(B <= 0 || steps < 0 || !d_seeds || !d_rs) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
+    int rc;
+    if(ctx->pending.size() > 4096) drain_events(ctx); // bound the timing-event backlog
+    if((rc = ensure_state(ctx, B)) != BIOIK_OK) return rc;
+    if((rc = ensure_schedules(ctx, std::max(steps, 1))) != BIOIK_OK) return rc;
+    const DProblem& P = ctx->hP;
+    DState S = ctx->S;
+    S.B = B;
+    S.C = ctx->cfg.population;
+    S.gens = ctx->cfg.generations;
+    S.memetic = ctx->cfg.memetic;
+    S.memetic_iters = ctx->cfg.memetic_iters;
+    S.total_steps = steps;
+    S.early_exit = early_exit;
+    if(!d_gp)
+    {
+        // no per-query parameters: broadcast the defaults of BioikGoal::p
+        if((rc = ensure_staging(ctx, B)) != BIOIK_OK) return rc;
+        for(int b = 0; b < B; b++) CU(ctx, cudaMemcpyAsync(ctx->d_gp + (size_t)b * P.G * GOAL_NPARAM, ctx->d_default_gp, (size_t)P.G * GOAL_NPARAM * 8, cudaMemcpyDeviceToDevice, st));
+        d_gp = ctx->d_gp;
+    }
+    S.goal_params = d_gp;
+    S.seeds = d_seeds;
+    S.rng_seeds = d_rs;
+    S.uniform = ctx->d_uniform;
+    S.gauss = ctx->d_gauss;
+    S.gauss_off = ctx->d_gauss_off;
+    S.rate_exp = ctx->d_rate_exp;
+
+    const int TPB = 128;
+    int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
+    EvolveSmem L{P.n, P.T, P.G};
+    const int warps_per_block = 4;
+    size_t smem = (size_t)warps_per_block * L.total() * sizeof(double);
+    if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int eblocks = (2 * B + warps_per_block - 1) / warps_per_block;
+
+    k_init<<<qblocks, TPB, 0, st>>>(ctx->dP, S);
+    if((rc = check_launch(ctx, "k_init")) != BIOIK_OK) return rc;
+    for(int step = 0; step < steps; step++)
+    {
+        EventPair s1 = get_pair(ctx, 1);
+        cudaEventRecord(s1.a, st);
+        k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S);
+        if((rc = check_launch(ctx, "k_prepare")) != BIOIK_OK) return rc;
+        cudaEventRecord(s1.b, st);
+        ctx->pending.push_back(s1);
+        EventPair ev = get_pair(ctx, 0);
+        cudaEventRecord(ev.a, st);
+        k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
+        if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
+        cudaEventRecord(ev.b, st);
+        ctx->pending.push_back(ev);
+        EventPair s2 = get_pair(ctx, 1);
+        cudaEventRecord(s2.a, st);
+        if(S.memetic)
+        {
+            k_memetic<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
+            if((rc = check_launch(ctx, "k_memetic")) != BIOIK_OK) return rc;
+        }
+        k_species<<<qblocks, TPB, 0, st>>>(ctx->dP, S, step);
+        if((rc = check_launch(ctx, "k_species")) != BIOIK_OK) return rc;
+        cudaEventRecord(s2.b, st);
+        ctx->pending.push_back(s2);
+    }
+    k_finalize<<<qblocks, TPB, 0, st>>>(ctx->dP, S, d_osol, d_ofit, d_osucc, d_osteps);
+    if((rc = check_launch(ctx, "k_finalize")) != BIOIK_OK) return rc;
+    return BIOIK_OK;
+}
+
+void drain_events_impl(bioik_ctx* ctx)
+{
+    for(auto& p : ctx->pending)
+    {
+        float ms = 0;
+        cudaEventSynchronize(p.b);
+        if(cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+        {
+            if(p.kind == 0)
+                ctx->ms_evolve += ms, ctx->n_evolve++;
+            else
+                ctx->ms_serial += ms, ctx->n_serial++;
+        }
+        ctx->pool.push_back(p);
+    }
+    ctx->pending.clear();
+}
+void drain_events(bioik_ctx* ctx) { drain_events_impl(ctx); }
+} // namespace
+
+extern "C" {
+
+int bioik_abi_version(void) { return BIOIK_ABI_VERSION; }
+
+const char* bioik_last_error(const bioik_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx** out)
+{
+    if(!robot || !cfg || !out) return fail(nullptr, BIOIK_E_INVALID, "null argument");
+    *out = nullptr;
+    if(cfg->population < 4 || cfg->population > 32 * EVOLVE_MAX_CPL) return fail(nullptr, BIOIK_E_LIMIT, "population must be in [4, 256]");
+    if(cfg->generations < 1 || cfg->memetic_iters < 0) return fail(nullptr, BIOIK_E_INVALID, "bad generations / memetic_iters");
+    if(cfg->memetic != 0 && cfg->memetic != 'q' && cfg->memetic != 'l') return fail(nullptr, BIOIK_E_INVALID, "memetic must be 0, 'q' or 'l'");
+    if(robot->n_links < 1 || robot->n_vars < 1) return fail(nullptr, BIOIK_E_INVALID, "empty robot");
+    bioik_ctx* ctx = new bioik_ctx();
+    ctx->cfg = *cfg;
+    {
+        std::string err;
+        int rc = intake_robot(robot, ctx->robot, err);
+        if(rc != BIOIK_OK)
+        {
+            delete ctx;
+            return fail(nullptr, rc, err);
+        }
+    }
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_uniform, sizeof(double) * 1024 * 1024 * 8);
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_gauss, sizeof(double) * 1024 * 1024 * 8);
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->dP, sizeof(DProblem));
+    if(e == cudaSuccess)
+    {
+        std::vector<double> u, g;
+        make_tables(cfg->table_seed, u, g);
+        e = cudaMemcpy(ctx->d_uniform, u.data(), u.size() * 8, cudaMemcpyHostToDevice);
+        if(e == cudaSuccess) e = cudaMemcpy(ctx->d_gauss, g.data(), g.size() * 8, cudaMemcpyHostToDevice);
+    }
+    if(e != cudaSuccess)
+    {
+        std::string msg = std::string("CUDA initialisation failed (no CPU fallback exists): ") + cudaGetErrorString(e);
+        bioik_destroy(ctx);
+        return fail(nullptr, BIOIK_E_CUDA, msg);
+    }
+    memset(&ctx->S, 0, sizeof(ctx->S));
+    *out = ctx;
+    return BIOIK_OK;
+}
+
+void bioik_destroy(bioik_ctx* ctx)
+{
+    if(!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if(ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for(auto& p : ctx->pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
+    for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
+    cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->state_block);
+    cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
+    if(ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
+{
+    if(!ctx || !problem) return fail(ctx, BIOIK_E_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_problem = false;
+    int rc = build_problem(ctx->robot, problem, ctx->hP, ctx->error);
+    if(rc != BIOIK_OK) return rc;
+    CU(ctx, cudaMemcpy(ctx->dP, &ctx->hP, sizeof(DProblem), cudaMemcpyHostToDevice));
+    std::vector<double> gp((size_t)problem->n_goals * GOAL_NPARAM);
+    for(int g = 0; g < problem->n_goals; g++)
+        for(int k = 0; k < GOAL_NPARAM; k++) gp[(size_t)g * GOAL_NPARAM + k] = problem->goals[g].p[k];
+    cudaFree(ctx->d_default_gp);
+    ctx->d_default_gp = nullptr;
+    CU(ctx, cudaMalloc(&ctx->d_default_gp, gp.size() * 8));
+    CU(ctx, cudaMemcpy(ctx->d_default_gp, gp.data(), gp.size() * 8, cudaMemcpyHostToDevice));
+    // state/staging/schedules depend on the problem shape: drop them
+    cudaFree(ctx->state_block);
+    ctx->state_block = nullptr;
+    ctx->capB = 0;
+    cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps);
+    ctx->d_gp = ctx->d_seeds = ctx->d_osol = ctx->d_ofit = nullptr;
+    ctx->d_rs = nullptr;
+    ctx->d_osucc = ctx->d_osteps = nullptr;
+    ctx->stageB = 0;
+    ctx->sched_steps = -1;
+    ctx->has_problem = true;
+    return BIOIK_OK;
+}
+
+int bioik_solve_batch_device(bioik_ctx* ctx, int32_t B, const double* d_goal_params, const double* d_seeds, const uint32_t* d_rng_seeds, int32_t steps, int32_t early_exit, double* d_out_solutions, double* d_out_fitness,
+                             int32_t* d_out_success, int32_t* d_out_steps, void* cuda_stream)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    return enqueue_solve(ctx, st, B, d_goal_params, d_seeds, d_rng_seeds, steps, early_exit, d_out_solutions, d_out_fitness, d_out_success, d_out_steps);
+}
+
+int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, double* out_solutions, double* out_fitness, int32_t* out_success,
+                      int32_t* out_steps)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    if(B <= 0 || !seeds || !rng_seeds) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    int rc = ensure_staging(ctx, B);
+    if(rc != BIOIK_OK) return rc;
+    const DProblem& P = ctx->hP;
+    cudaStream_t st = ctx->stream;
+    if(goal_params) CU(ctx, cudaMemcpyAsync(ctx->d_gp, goal_params, (size_t)B * P.G * GOAL_NPARAM * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_seeds, seeds, (size_t)B * P.n_vars * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_rs, rng_seeds, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+    if(rc != BIOIK_OK) return rc;
+    if(out_solutions) CU(ctx, cudaMemcpyAsync(out_solutions, ctx->d_osol, (size_t)B * P.n_vars * 8, cudaMemcpyDeviceToHost, st));
+    if(out_fitness) CU(ctx, cudaMemcpyAsync(out_fitness, ctx->d_ofit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if(out_success) CU(ctx, cudaMemcpyAsync(out_success, ctx->d_osucc, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_osteps, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    drain_events(ctx);
+    return BIOIK_OK;
+}
+
+int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, double* out_genes, double* out_gradients, double* out_species_fitness,
+                            double* out_solutions, double* out_fitness)
+{
+    int rc = bioik_solve_batch(ctx, B, goal_params, seeds, rng_seeds, steps, 0, out_solutions, out_fitness, nullptr, nullptr);
+    if(rc != BIOIK_OK) return rc;
+    size_t n = ctx->hP.n;
+    if(out_genes) CU(ctx, cudaMemcpy(out_genes, ctx->S.genes, (size_t)B * 4 * n * 8, cudaMemcpyDeviceToHost));
+    if(out_gradients) CU(ctx, cudaMemcpy(out_gradients, ctx->S.grads, (size_t)B * 4 * n * 8, cudaMemcpyDeviceToHost));
+    if(out_species_fitness) CU(ctx, cudaMemcpy(out_species_fitness, ctx->S.sfit, (size_t)B * 2 * 8, cudaMemcpyDeviceToHost));
+    return BIOIK_OK;
+}
+
+int bioik_synchronize(bioik_ctx* ctx)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BIOIK_OK;
+}
+
+int bioik_fk_batch(bioik_ctx* ctx, int32_t B, const double* variables, double* out_tip_frames)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const DProblem& P = ctx->hP;
+    double *dv = nullptr, *dt = nullptr;
+    CU(ctx, cudaMalloc(&dv, (size_t)B * P.n_vars * 8));
+    CU(ctx, cudaMalloc(&dt, (size_t)B * P.T * 7 * 8));
+    CU(ctx, cudaMemcpyAsync(dv, variables, (size_t)B * P.n_vars * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_fk_batch<<<(B + 127) / 128, 128, 0, ctx->stream>>>(ctx->dP, B, dv, dt);
+    int rc = check_launch(ctx, "k_fk_batch");
+    if(rc == BIOIK_OK)
+    {
+        cudaError_t e = cudaMemcpyAsync(out_tip_frames, dt, (size_t)B * P.T * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if(e != cudaSuccess) rc = fail(ctx, BIOIK_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dv), cudaFree(dt);
+    return rc;
+}
+
+int bioik_approx_batch(bioik_ctx* ctx, int32_t B, const double* variables, double* out_delta_frames)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const DProblem& P = ctx->hP;
+    double *dv = nullptr, *dd = nullptr;
+    size_t dn = (size_t)B * P.T * P.n * 7 * 8;
+    CU(ctx, cudaMalloc(&dv, (size_t)B * P.n_vars * 8));
+    CU(ctx, cudaMalloc(&dd, dn));
+    CU(ctx, cudaMemcpyAsync(dv, variables, (size_t)B * P.n_vars * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_approx_batch<<<(B + 127) / 128, 128, 0, ctx->stream>>>(ctx->dP, B, dv, dd);
+    int rc = check_launch(ctx, "k_approx_batch");
+    if(rc == BIOIK_OK)
+    {
+        cudaError_t e = cudaMemcpyAsync(out_delta_frames, dd, dn, cudaMemcpyDeviceToHost, ctx->stream);
+        if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if(e != cudaSuccess) rc = fail(ctx, BIOIK_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dv), cudaFree(dd);
+    return rc;
+}
+
+int bioik_approx_fitness_batch(bioik_ctx* ctx, int32_t B, int32_t M, const double* goal_params, const double* seeds, const double* base_variables, const double* genotypes, double* out_primary, double* out_secondary)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const DProblem& P = ctx->hP;
+    size_t ngp = (size_t)B * P.G * GOAL_NPARAM, nv = (size_t)B * P.n_vars, ng = (size_t)B * M * P.n, nf = (size_t)B * M;
+    std::vector<double> gp_host;
+    if(!goal_params)
+    {
+        gp_host.resize(ngp);
+        std::vector<double> def((size_t)P.G * GOAL_NPARAM);
+        cudaMemcpy(def.data(), ctx->d_default_gp, def.size() * 8, cudaMemcpyDeviceToHost);
+        for(int b = 0; b < B; b++) std::copy(def.begin(), def.end(), gp_host.begin() + (size_t)b * def.size());
+        goal_params = gp_host.data();
+    }
+    double *d_gp = nullptr, *d_seed = nullptr, *d_base = nullptr, *d_gen = nullptr, *d_p = nullptr, *d_s = nullptr, *d_scr = nullptr;
+    CU(ctx, cudaMalloc(&d_gp, ngp * 8));
+    CU(ctx, cudaMalloc(&d_seed, nv * 8));
+    CU(ctx, cudaMalloc(&d_base, nv * 8));
+    CU(ctx, cudaMalloc(&d_gen, ng * 8));
+    CU(ctx, cudaMalloc(&d_p, nf * 8));
+    CU(ctx, cudaMalloc(&d_s, nf * 8));
+    CU(ctx, cudaMalloc(&d_scr, nf * P.T * P.n * 7 * 8));
+    cudaStream_t st = ctx->stream;
+    CU(ctx, cudaMemcpyAsync(d_gp, goal_params, ngp * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_seed, seeds, nv * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_base, base_variables, nv * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(d_gen, genotypes, ng * 8, cudaMemcpyHostToDevice, st));
+    k_approx_fitness<<<(int)((nf + 127) / 128), 128, 0, st>>>(ctx->dP, B, M, d_gp, d_seed, d_base, d_gen, d_p, d_s, d_scr);
+    int rc = check_launch(ctx, "k_approx_fitness");
+    if(rc == BIOIK_OK)
+    {
+        cudaError_t e = cudaSuccess;
+        if(out_primary) e = cudaMemcpyAsync(out_primary, d_p, nf * 8, cudaMemcpyDeviceToHost, st);
+        if(e == cudaSuccess && out_secondary) e = cudaMemcpyAsync(out_secondary, d_s, nf * 8, cudaMemcpyDeviceToHost, st);
+        if(e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if(e != cudaSuccess) rc = fail(ctx, BIOIK_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_gp), cudaFree(d_seed), cudaFree(d_base), cudaFree(d_gen), cudaFree(d_p), cudaFree(d_s), cudaFree(d_scr);
+    return rc;
+}
+
+int64_t bioik_launch_count(const bioik_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int64_t* out_launches_evolve, double* out_ms_serial, int64_t* out_launches_serial)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    drain_events(ctx);
+    if(out_ms_evolve) *out_ms_evolve = ctx->ms_evolve;
+    if(out_launches_evolve) *out_launches_evolve = ctx->n_evolve;
+    if(out_ms_serial) *out_ms_serial = ctx->ms_serial;
+    if(out_launches_serial) *out_launches_serial = ctx->n_serial;
+    if(reset)
+    {
+        ctx->ms_evolve = ctx->ms_serial = 0;
+        ctx->n_evolve = ctx->n_serial = 0;
+    }
+    return BIOIK_OK;
+}
+}

@@ -1,0 +1,667 @@
+// bioik_dev.cuh — per-thread device functions of the B200 bio2/bio2_memetic path.
+//
+// Arithmetic contract: IEEE binary64, no implicit FMA contraction
+// (nvcc -fmad=false), explicit __fma_rn only where the reference's AVX+FMA
+// approximator fuses (src/forward_kinematics.h:949-950,1091-1092) and inside
+// d_sincos.  Every function below states the reference lines it implements and
+// keeps their operation ORDER, so results are bit-identical to an IEEE-strict
+// CPU evaluation of the same formulas.
+//
+// The functions are written against plain pointers (global or shared memory) so
+// that tests/hostsim can compile this header with g++ (BIOIK_HOSTSIM) and check
+// the per-thread logic without a GPU.  That build is test-only: the shipped
+// library contains CUDA kernels only.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef BIOIK_HOSTSIM
+#include <cmath>
+#define BIOIK_HD inline
+#define BIOIK_FMA(a, b, c) std::fma((a), (b), (c))
+#define BIOIK_RINT(x) std::rint(x)
+#define BIOIK_FMOD(x, y) std::fmod((x), (y))
+#define BIOIK_SQRT(x) std::sqrt(x)
+#define BIOIK_FABS(x) std::fabs(x)
+#define BIOIK_FMIN(a, b) std::fmin((a), (b))
+#define BIOIK_FMAX(a, b) std::fmax((a), (b))
+#define BIOIK_ATAN2(a, b) std::atan2((a), (b))
+#define BIOIK_ACOS(a) std::acos(a)
+#else
+#define BIOIK_HD __device__ __forceinline__
+#define BIOIK_FMA(a, b, c) __fma_rn((a), (b), (c))
+#define BIOIK_RINT(x) rint(x)
+#define BIOIK_FMOD(x, y) fmod((x), (y))
+#define BIOIK_SQRT(x) sqrt(x)
+#define BIOIK_FABS(x) fabs(x)
+#define BIOIK_FMIN(a, b) fmin((a), (b))
+#define BIOIK_FMAX(a, b) fmax((a), (b))
+#define BIOIK_ATAN2(a, b) atan2((a), (b))
+#define BIOIK_ACOS(a) acos(a)
+#endif
+
+namespace bioik
+{
+
+// compiled-in capacities (BIOIK_E_LIMIT beyond)
+constexpr int MAX_VARS = 64;   // robot variables
+constexpr int MAX_GENES = 48;  // active variables
+constexpr int MAX_SLOTS = 96;  // links in the FK schedule
+constexpr int MAX_TIPS = 8;
+constexpr int MAX_GOALS = 16;
+constexpr int GOAL_NPARAM = 12;
+constexpr double DBLMAX = 1.7976931348623157e308;
+
+enum JointType { J_FIXED = 0, J_REVOLUTE = 1, J_PRISMATIC = 2, J_FLOATING = 3, J_PLANAR = 4 };
+enum GoalType {
+    G_POSITION = 1, G_ORIENTATION, G_POSE, G_LOOK_AT, G_MAX_DISTANCE, G_MIN_DISTANCE, G_LINE, G_PLANE, G_AVOID_JOINT_LIMITS,
+    G_CENTER_JOINTS, G_REGULARIZATION, G_MINIMAL_DISPLACEMENT, G_JOINT_VARIABLE, G_SIDE, G_DIRECTION
+};
+
+// ---------------------------------------------------------------------------
+// Flattened problem (device constant data; built by the host in bioik_capi.cu)
+// ---------------------------------------------------------------------------
+struct DSlot // one scheduled link (src/forward_kinematics.h:268-282 order)
+{
+    int32_t parent; // schedule slot of the parent link, -1 for the root
+    int32_t type;   // JointType of the parent joint
+    int32_t var;    // first variable index, -1 if none
+    int32_t tipmask; // bit t set: tip t depends on this joint (tip_dependencies, :588-598)
+    double origin[7];
+    double axis[3];
+};
+struct DGene // one active variable (problem.active_variables order)
+{
+    int32_t var;       // robot variable index
+    int32_t dep_start; // range in DProblem::dep_* (joint_dependencies of the variable's joint, :570-587)
+    int32_t dep_count; // 0 if the variable's own joint mimics another joint (:623)
+    int32_t pad;
+    double clip_min, clip_max, span, vmin, vmax, vel_weight; // robot_info.h:48-55, problem.cpp:206-225
+};
+struct DGoal
+{
+    int32_t type, tip, secondary, var_index; // var_index: gene index or -1-robot_var (goal.h:70-77)
+    double weight_sq;
+};
+struct DMimic
+{
+    int32_t dest, src;
+    double factor, offset;
+};
+struct DProblem
+{
+    int32_t n_vars, n, T, L, G, n_mimic, has_secondary, pad;
+    double dpos, drot, dtwist;
+    int32_t tip_slot[MAX_TIPS];
+    int32_t gene_of_var[MAX_VARS]; // -1 if inactive
+    DSlot slots[MAX_SLOTS];
+    DGene genes[MAX_GENES];
+    DGoal goals[MAX_GOALS];
+    DMimic mimics[MAX_VARS];
+    int32_t dep_slot[MAX_SLOTS + MAX_GENES];
+    double dep_scale[MAX_SLOTS + MAX_GENES];
+};
+
+// ---------------------------------------------------------------------------
+// frames as 7 doubles: px py pz qx qy qz qw   (include/bio_ik/frame.h)
+// ---------------------------------------------------------------------------
+struct V3 { double x, y, z; };
+struct Q4 { double x, y, z, w; };
+struct F7 { V3 p; Q4 q; };
+
+BIOIK_HD F7 load_frame(const double* f) { return F7{{f[0], f[1], f[2]}, {f[3], f[4], f[5], f[6]}}; }
+BIOIK_HD void store_frame(double* f, const F7& a)
+{
+    f[0] = a.p.x; f[1] = a.p.y; f[2] = a.p.z; f[3] = a.q.x; f[4] = a.q.y; f[5] = a.q.z; f[6] = a.q.w;
+}
+
+// include/bio_ik/frame.h:108-149.  The early-out (:122-126) returns exactly what the
+// arithmetic below produces for those inputs (up to the sign of zero), so it is dropped.
+BIOIK_HD V3 quat_mul_vec(const Q4& q, const V3& v)
+{
+    double t_x = q.y * v.z - q.z * v.y;
+    double t_y = q.z * v.x - q.x * v.z;
+    double t_z = q.x * v.y - q.y * v.x;
+    double r_x = q.w * t_x + q.y * t_z - q.z * t_y;
+    double r_y = q.w * t_y + q.z * t_x - q.x * t_z;
+    double r_z = q.w * t_z + q.x * t_y - q.y * t_x;
+    r_x += r_x; r_y += r_y; r_z += r_z;
+    r_x += v.x; r_y += v.y; r_z += v.z;
+    return V3{r_x, r_y, r_z};
+}
+// include/bio_ik/frame.h:151-172
+BIOIK_HD Q4 quat_mul_quat(const Q4& p, const Q4& q)
+{
+    Q4 r;
+    r.x = (p.w * q.x + p.x * q.w) + (p.y * q.z - p.z * q.y);
+    r.y = (p.w * q.y - p.x * q.z) + (p.y * q.w + p.z * q.x);
+    r.z = (p.w * q.z + p.x * q.y) - (p.y * q.x - p.z * q.w);
+    r.w = (p.w * q.w - p.x * q.x) - (p.y * q.y + p.z * q.z);
+    return r;
+}
+// tf2::operator*(Quaternion, Quaternion), left-to-right (used by computeJacobian :648,:680)
+BIOIK_HD Q4 tf2_mul(const Q4& a, const Q4& b)
+{
+    Q4 r;
+    r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+    r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+    r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+    r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+    return r;
+}
+BIOIK_HD Q4 quat_inv(const Q4& q) { return Q4{-q.x, -q.y, -q.z, q.w}; }
+// include/bio_ik/frame.h:174-180
+BIOIK_HD F7 concat(const F7& a, const F7& b)
+{
+    V3 d = quat_mul_vec(a.q, b.p);
+    F7 r;
+    r.p = V3{a.p.x + d.x, a.p.y + d.y, a.p.z + d.z};
+    r.q = quat_mul_quat(a.q, b.q);
+    return r;
+}
+
+// The quat_mul_vec early-out matters in ONE way: when v == 0 or q == identity the
+// reference returns v itself.  The arithmetic path returns the same VALUE; only a
+// negative zero could differ, and no later operation distinguishes signed zeros.
+
+// d_sincos: arithmetic-contract sin/cos of the half joint angle
+// (src/forward_kinematics.h:99-104): Cody–Waite reduction by pi/2 with explicit FMA,
+// fdlibm minimax polynomials; identical operation sequence on CPU oracle and GPU.
+BIOIK_HD void d_sincos(double x, double& s_out, double& c_out)
+{
+    if(!(BIOIK_FABS(x) <= 1.0e5)) x = BIOIK_FMOD(x, 6.283185307179586);
+    double fn = BIOIK_RINT(x * 0.6366197723675814);
+    double r = BIOIK_FMA(fn, -1.5707963267948966, x);
+    r = BIOIK_FMA(fn, -6.123233995736766e-17, r);
+    r = BIOIK_FMA(fn, 1.4973849048591698e-33, r);
+    double z = r * r;
+    double ps = BIOIK_FMA(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = BIOIK_FMA(z, ps, 2.75573137070700676789e-06);
+    ps = BIOIK_FMA(z, ps, -1.98412698298579493134e-04);
+    ps = BIOIK_FMA(z, ps, 8.33333333332248946124e-03);
+    ps = BIOIK_FMA(z, ps, -1.66666666666666324348e-01);
+    double sr = BIOIK_FMA(r * z, ps, r);
+    double pc = BIOIK_FMA(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = BIOIK_FMA(z, pc, -2.75573143513906633035e-07);
+    pc = BIOIK_FMA(z, pc, 2.48015872894767294178e-05);
+    pc = BIOIK_FMA(z, pc, -1.38888888888741095749e-03);
+    pc = BIOIK_FMA(z, pc, 4.16666666666666019037e-02);
+    double cr = BIOIK_FMA(z * z, pc, BIOIK_FMA(z, -0.5, 1.0));
+    long long q = (long long)fn;
+    double s = (q & 1) ? cr : sr;
+    double c = (q & 1) ? sr : cr;
+    if(q & 2) s = -s;
+    if((q + 1) & 2) c = -c;
+    s_out = s;
+    c_out = c;
+}
+
+// src/utils.h:319
+BIOIK_HD double mix(double a, double b, double f) { return a * (1.0 - f) + b * f; }
+// src/utils.h:321-326 / robot_info.h:61-66 (NaN passes through, like the reference)
+BIOIK_HD double clampd(double v, double lo, double hi)
+{
+    if(v < lo) v = lo;
+    if(v > hi) v = hi;
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// variable vector of a task: seed with the active entries replaced by genes
+// (genesToJointVariables, src/ik_evolution_2.cpp:101-107) then updateMimic
+// (src/forward_kinematics.h:230-246)
+// ---------------------------------------------------------------------------
+BIOIK_HD void assemble_variables(const DProblem& P, const double* seed, const double* genes, double* vars)
+{
+    for(int v = 0; v < P.n_vars; v++)
+    {
+        int g = P.gene_of_var[v];
+        vars[v] = g >= 0 ? genes[g] : seed[v];
+    }
+    for(int m = 0; m < P.n_mimic; m++) vars[P.mimics[m].dest] = vars[P.mimics[m].src] * P.mimics[m].factor + P.mimics[m].offset;
+}
+
+// joint-local frame, src/forward_kinematics.h:78-139
+BIOIK_HD F7 joint_frame(const DSlot& S, const double* vars)
+{
+    F7 f;
+    f.p = V3{0.0, 0.0, 0.0};
+    f.q = Q4{0.0, 0.0, 0.0, 1.0};
+    if(S.type == J_REVOLUTE)
+    {
+        double half_angle = vars[S.var] * 0.5;
+        double fs, fc;
+        d_sincos(half_angle, fs, fc);
+        f.q = Q4{S.axis[0] * fs, S.axis[1] * fs, S.axis[2] * fs, fc};
+    }
+    else if(S.type == J_PRISMATIC)
+    {
+        double v = vars[S.var];
+        f.p = V3{S.axis[0] * v, S.axis[1] * v, S.axis[2] * v};
+    }
+    return f;
+}
+
+// RobotFK_Fast_Base::applyConfiguration, src/forward_kinematics.h:331-354.
+// frames: [L][7] scratch (global frames of the scheduled links).
+BIOIK_HD void exact_fk(const DProblem& P, const double* vars, double* frames)
+{
+    for(int s = 0; s < P.L; s++)
+    {
+        const DSlot& S = P.slots[s];
+        F7 jf = joint_frame(S, vars);
+        F7 o = load_frame(S.origin);
+        F7 r;
+        if(S.parent >= 0)
+            r = concat(concat(load_frame(frames + 7 * S.parent), o), jf);
+        else
+            r = concat(o, jf);
+        store_frame(frames + 7 * s, r);
+    }
+}
+
+// RobotFK_Jacobian::computeJacobian (src/forward_kinematics.h:600-730) fused with
+// RobotFK_Mutator::initializeMutationApproximator (:802-930) for one (gene, tip):
+// returns the delta frame; *masked = the :919-926 test.
+BIOIK_HD F7 delta_frame(const DProblem& P, const double* frames, int gene, int tip, bool& masked)
+{
+    const DGene& Gn = P.genes[gene];
+    F7 tipf = load_frame(frames + 7 * P.tip_slot[tip]);
+    double j0 = 0, j1 = 0, j2 = 0, j3 = 0, j4 = 0, j5 = 0;
+    for(int d = 0; d < Gn.dep_count; d++)
+    {
+        int s = P.dep_slot[Gn.dep_start + d];
+        double scale = P.dep_scale[Gn.dep_start + d];
+        const DSlot& S = P.slots[s];
+        if(!((S.tipmask >> tip) & 1)) continue;
+        F7 lf = load_frame(frames + 7 * s);
+        if(S.type == J_REVOLUTE)
+        {
+            Q4 q = tf2_mul(quat_inv(lf.q), tipf.q); // :648
+            q = quat_inv(q);                        // :649
+            V3 rot = quat_mul_vec(q, V3{S.axis[0], S.axis[1], S.axis[2]}); // :651-652
+            V3 vel = V3{lf.p.x - tipf.p.x, lf.p.y - tipf.p.y, lf.p.z - tipf.p.z}; // :654
+            vel = quat_mul_vec(quat_inv(tipf.q), vel);                            // :655
+            V3 c = V3{vel.y * rot.z - vel.z * rot.y, vel.z * rot.x - vel.x * rot.z, vel.x * rot.y - vel.y * rot.x}; // :657
+            j0 += c.x * scale; j1 += c.y * scale; j2 += c.z * scale;
+            j3 += rot.x * scale; j4 += rot.y * scale; j5 += rot.z * scale;
+        }
+        else if(S.type == J_PRISMATIC)
+        {
+            Q4 q = tf2_mul(quat_inv(lf.q), tipf.q); // :680
+            q = quat_inv(q);
+            V3 v = quat_mul_vec(q, V3{S.axis[0], S.axis[1], S.axis[2]}); // :685
+            j0 += v.x * scale; j1 += v.y * scale; j2 += v.z * scale;
+        }
+    }
+    F7 d;
+    d.p = quat_mul_vec(tipf.q, V3{j0, j1, j2}); // :833-838
+    Q4 q = quat_mul_quat(tipf.q, Q4{j3 * 0.5, j4 * 0.5, j5 * 0.5, 1.0}); // :842-847
+    d.q = Q4{q.x - tipf.q.x, q.y - tipf.q.y, q.z - tipf.q.z, q.w - tipf.q.w}; // :848
+    masked = (d.p.x != 0.0) | (d.p.y != 0.0) | (d.p.z != 0.0) | (d.q.x != 0.0) | (d.q.y != 0.0) | (d.q.z != 0.0); // :919-926
+    // A gene outside mutation_approx_map contributes nothing (:1083,:1198); a zero delta frame
+    // makes the dense loops below add exactly 0.
+    if(!masked) d.q.w = 0.0;
+    return d;
+}
+
+// computeApproximateMutations for one genotype, src/forward_kinematics.h:1061-1110 (AVX+FMA form).
+// tip0 [T][7], delta [T][n][7] (zero where unmasked), base [n], x [n] -> out [T][7]
+BIOIK_HD void approx_frames(int T, int n, const double* tip0, const double* delta, const double* base, const double* x, double* out)
+{
+    for(int t = 0; t < T; t++)
+    {
+        double f0 = tip0[7 * t + 0], f1 = tip0[7 * t + 1], f2 = tip0[7 * t + 2], f3 = tip0[7 * t + 3], f4 = tip0[7 * t + 4], f5 = tip0[7 * t + 5], f6 = tip0[7 * t + 6];
+        const double* D = delta + (size_t)t * n * 7;
+        for(int i = 0; i < n; i++)
+        {
+            double d = x[i] - base[i]; // :1086
+            f0 = BIOIK_FMA(d, D[7 * i + 0], f0);
+            f1 = BIOIK_FMA(d, D[7 * i + 1], f1);
+            f2 = BIOIK_FMA(d, D[7 * i + 2], f2);
+            f3 = BIOIK_FMA(d, D[7 * i + 3], f3);
+            f4 = BIOIK_FMA(d, D[7 * i + 4], f4);
+            f5 = BIOIK_FMA(d, D[7 * i + 5], f5);
+            f6 = BIOIK_FMA(d, D[7 * i + 6], f6);
+        }
+        out[7 * t + 0] = f0; out[7 * t + 1] = f1; out[7 * t + 2] = f2; out[7 * t + 3] = f3; out[7 * t + 4] = f4; out[7 * t + 5] = f5; out[7 * t + 6] = f6;
+    }
+}
+
+// computeApproximateMutation1, src/forward_kinematics.h:933-964 (AVX+FMA form), with the
+// intended semantics for tips the variable does not influence (zero delta => copy)
+BIOIK_HD void approx_frames1(int T, int n, const double* delta, int gene, double dv, const double* in, double* out)
+{
+    for(int t = 0; t < T; t++)
+    {
+        const double* D = delta + ((size_t)t * n + gene) * 7;
+        for(int k = 0; k < 7; k++) out[7 * t + k] = BIOIK_FMA(dv, D[k], in[7 * t + k]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Goal::evaluate bodies (include/bio_ik/goal_types.h) * weight_sq, summed in goal
+// order (src/problem.cpp:244-257).  tips [T][7], x [n] genes, gp [G][NPARAM] per-query
+// goal parameters, seed [n_vars] = Problem::initial_guess.
+// which: 0 = primary goals, 1 = secondary goals.
+// ---------------------------------------------------------------------------
+BIOIK_HD double len2(double x, double y, double z) { return x * x + y * y + z * z; }
+BIOIK_HD double qlen2(double x, double y, double z, double w) { return x * x + y * y + z * z + w * w; }
+
+BIOIK_HD double goal_value(const DProblem& P, const DGoal& g, const double* p, const double* tips, const double* x, const double* seed)
+{
+    const double* f = tips + 7 * g.tip;
+    switch(g.type)
+    {
+    case G_POSITION: // goal_types.h:96: tf2 distance2(v) = (v - this).length2()
+        return len2(p[0] - f[0], p[1] - f[1], p[2] - f[2]);
+    case G_ORIENTATION: // goal_types.h:119
+        return BIOIK_FMIN(qlen2(p[3] - f[3], p[4] - f[4], p[5] - f[5], p[6] - f[6]), qlen2(p[3] + f[3], p[4] + f[4], p[5] + f[5], p[6] + f[6]));
+    case G_POSE: // goal_types.h:149-180
+    {
+        double e = 0.0;
+        e += len2(p[0] - f[0], p[1] - f[1], p[2] - f[2]);
+        e += BIOIK_FMIN(qlen2(p[3] - f[3], p[4] - f[4], p[5] - f[5], p[6] - f[6]), qlen2(p[3] + f[3], p[4] + f[4], p[5] + f[5], p[6] + f[6])) * (p[7] * p[7]);
+        return e;
+    }
+    case G_LOOK_AT: // goal_types.h:204-211
+    {
+        V3 axis = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[0], p[1], p[2]});
+        double ax = p[3] - f[0], ay = p[4] - f[1], az = p[5] - f[2];
+        double sa = 1.0 / BIOIK_SQRT(len2(ax, ay, az));
+        ax = ax * sa; ay = ay * sa; az = az * sa;
+        double sb = 1.0 / BIOIK_SQRT(len2(axis.x, axis.y, axis.z));
+        double bx = axis.x * sb, by = axis.y * sb, bz = axis.z * sb;
+        return len2(bx - ax, by - ay, bz - az);
+    }
+    case G_MAX_DISTANCE: // goal_types.h:235-240
+    {
+        double d = BIOIK_FMAX(0.0, BIOIK_SQRT(len2(p[0] - f[0], p[1] - f[1], p[2] - f[2])) - p[3]);
+        return d * d;
+    }
+    case G_MIN_DISTANCE: // goal_types.h:264-269
+    {
+        double d = BIOIK_FMAX(0.0, p[3] - BIOIK_SQRT(len2(p[0] - f[0], p[1] - f[1], p[2] - f[2])));
+        return d * d;
+    }
+    case G_LINE: // goal_types.h:293-297
+    {
+        double rx = f[0] - p[0], ry = f[1] - p[1], rz = f[2] - p[2];
+        double k = p[3] * rx + p[4] * ry + p[5] * rz; // direction.dot(fb.pos - position)
+        double qx = f[0] - p[3] * k, qy = f[1] - p[4] * k, qz = f[2] - p[5] * k;
+        return len2(qx - p[0], qy - p[1], qz - p[2]);
+    }
+    case G_PLANE: // goal_types.h:321-327
+    {
+        double sd = (f[0] - p[0]) * p[3] + (f[1] - p[1]) * p[4] + (f[2] - p[2]) * p[5];
+        return sd * sd;
+    }
+    case G_AVOID_JOINT_LIMITS: // goal_types.h:387-401
+    {
+        double sum = 0.0;
+        for(int i = 0; i < P.n; i++)
+        {
+            const DGene& Gn = P.genes[i];
+            if(Gn.clip_max == DBLMAX) continue;
+            double d = x[i] - (Gn.vmin + Gn.vmax) * 0.5;
+            d = BIOIK_FMAX(0.0, BIOIK_FABS(d) * 2.0 - Gn.span * 0.5);
+            d *= Gn.vel_weight;
+            sum += d * d;
+        }
+        return sum;
+    }
+    case G_CENTER_JOINTS: // goal_types.h:412-425
+    {
+        double sum = 0.0;
+        for(int i = 0; i < P.n; i++)
+        {
+            const DGene& Gn = P.genes[i];
+            if(Gn.clip_max == DBLMAX) continue;
+            double d = x[i] - (Gn.vmin + Gn.vmax) * 0.5;
+            d *= Gn.vel_weight;
+            sum += d * d;
+        }
+        return sum;
+    }
+    case G_REGULARIZATION: // goal_types.h:435-444
+    {
+        double sum = 0.0;
+        for(int i = 0; i < P.n; i++)
+        {
+            double d = x[i] - seed[P.genes[i].var];
+            sum += d * d;
+        }
+        return sum;
+    }
+    case G_MINIMAL_DISPLACEMENT: // goal_types.h:455-465
+    {
+        double sum = 0.0;
+        for(int i = 0; i < P.n; i++)
+        {
+            double d = x[i] - seed[P.genes[i].var];
+            d *= P.genes[i].vel_weight;
+            sum += d * d;
+        }
+        return sum;
+    }
+    case G_JOINT_VARIABLE: // goal_types.h:494-498
+    {
+        double v = g.var_index >= 0 ? x[g.var_index] : seed[-1 - g.var_index];
+        double d = p[0] - v;
+        return d * d;
+    }
+    case G_SIDE: // goal_types.h:606-613
+    {
+        V3 v = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[0], p[1], p[2]});
+        double s = BIOIK_FMAX(0.0, v.x * p[3] + v.y * p[4] + v.z * p[5]);
+        return s * s;
+    }
+    case G_DIRECTION: // goal_types.h:637-643
+    {
+        V3 v = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[0], p[1], p[2]});
+        return len2(p[3] - v.x, p[4] - v.y, p[5] - v.z);
+    }
+    default: return 0.0;
+    }
+}
+
+// IKBase::null_tip_frames (src/ik_base.h:135,160,163): what secondary goals receive instead of
+// tip frames.  Uninitialised memory in the reference; identity frames here and in the oracle.
+#ifdef BIOIK_HOSTSIM
+static const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+#else
+static __device__ const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+#endif
+
+BIOIK_HD double goal_fitness(const DProblem& P, int which, const double* gp, const double* tips, const double* x, const double* seed)
+{
+    if(!tips) tips = NULL_TIPS;
+    double sum = 0.0;
+    for(int g = 0; g < P.G; g++)
+    {
+        if(P.goals[g].secondary != which) continue;
+        sum += goal_value(P, P.goals[g], gp + g * GOAL_NPARAM, tips, x, seed) * P.goals[g].weight_sq;
+    }
+    return sum;
+}
+
+// ---------------------------------------------------------------------------
+// reproduce() for one child, src/ik_evolution_2.cpp:263-301.
+//   g0 = parent genes, gr0/gr1 = the two parents' gradients, rr = this child's gaussian
+//   slab, rate_exp = fast_random_index(16) of this child.
+// ---------------------------------------------------------------------------
+BIOIK_HD void reproduce_child(const DProblem& P, int child_index, int rate_exp, const double* rr, const double* g0, const double* gr0, const double* gr1, double* child_genes, double* child_grads)
+{
+    double mutation_rate = (double)(1 << rate_exp) * (1.0 / (double)(1 << 23)); // :265
+    double fmix = (child_index % 2 == 0) ? 0.2 : 0.0;                           // :268  (bool * 0.2)
+    double gradient_factor = (double)(child_index % 3);                        // :269
+    for(int i = 0; i < P.n; i++)
+    {
+        const DGene& Gn = P.genes[i];
+        double r = rr[i];
+        double f = mutation_rate * Gn.span;
+        double gene = g0[i];
+        double parent_gene = gene;
+        gene += r * f;
+        double parent_gradient = mix(gr0[i], gr1[i], fmix);
+        double gradient = parent_gradient * gradient_factor;
+        gene += gradient;
+        gene = clampd(gene, Gn.clip_min, Gn.clip_max);
+        child_genes[i] = gene;
+        if(child_grads) child_grads[i] = mix(parent_gradient, gene - parent_gene, 0.3);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// RNG pieces that run on the device (src/ik_base.h:49-126)
+// ---------------------------------------------------------------------------
+// std::minstd_rand: x <- 48271 x mod 2147483647
+BIOIK_HD uint32_t minstd_next(uint32_t& s)
+{
+    s = (uint32_t)(((uint64_t)s * 48271ull) % 2147483647ull);
+    return s;
+}
+// std::uniform_real_distribution<double>(0,1)(minstd) = generate_canonical<double,53>: two draws
+// (libstdc++ bits/random.tcc): sum = (a-1) + (b-1)*R, R = 2147483646; ret = sum / R^2
+BIOIK_HD double minstd_uniform01(uint32_t& s)
+{
+    double a = (double)(minstd_next(s) - 1u);
+    double b = (double)(minstd_next(s) - 1u);
+    double sum = a * 1.0;           // __sum += (urng()-min) * __tmp, __tmp = 1
+    sum = sum + b * 2147483646.0;   // __tmp = R
+    double ret = sum / 4611686009837453316.0; // R*R rounded to double (4611686009837453316 = 2147483646^2 is exact below 2^63; double rounding below)
+    if(ret >= 1.0) ret = 0.99999999999999989; // nextafter(1, 0)
+    return ret;
+}
+// Random::random(min, max), src/ik_base.h:64
+BIOIK_HD double minstd_random(uint32_t& s, double lo, double hi) { return minstd_uniform01(s) * (hi - lo) + lo; }
+// std::uniform_int_distribution<size_t>(0, n-1)(minstd) for n-1 < 2147483645 (libstdc++ bits/uniform_int_dist.h, downscaling branch)
+BIOIK_HD uint32_t minstd_index(uint32_t& s, uint32_t n)
+{
+    const uint64_t urngrange = 2147483645ull;
+    uint64_t uerange = (uint64_t)n; // urange + 1
+    uint64_t scaling = urngrange / uerange;
+    uint64_t past = uerange * scaling;
+    uint64_t ret;
+    do
+        ret = (uint64_t)minstd_next(s) - 1ull;
+    while(ret >= past);
+    return (uint32_t)(ret / scaling);
+}
+
+// ---------------------------------------------------------------------------
+// Problem::checkSolutionActiveVariables, src/problem.cpp:259-341 (KDL semantics per
+// SURVEY.md Appendix C).  Thresholds are compared against 1e-5-scale quantities; the
+// libm-class functions here (atan2, acos, sqrt) are not part of the bit-exact contract.
+// ---------------------------------------------------------------------------
+BIOIK_HD void quat_to_matrix(const Q4& q, double* R)
+{
+    double x = q.x, y = q.y, z = q.z, w = q.w;
+    double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
+    R[0] = w2 + x2 - y2 - z2; R[1] = 2 * x * y - 2 * w * z; R[2] = 2 * x * z + 2 * w * y;
+    R[3] = 2 * x * y + 2 * w * z; R[4] = w2 - x2 + y2 - z2; R[5] = 2 * y * z - 2 * w * x;
+    R[6] = 2 * x * z - 2 * w * y; R[7] = 2 * y * z + 2 * w * x; R[8] = w2 - x2 - y2 + z2;
+}
+BIOIK_HD void kdl_twist(const F7& fa, const F7& fb, double* vel, double* rot)
+{
+    double Ra[9], Rb[9], M[9];
+    quat_to_matrix(fa.q, Ra);
+    quat_to_matrix(fb.q, Rb);
+    double d0 = fb.p.x - fa.p.x, d1 = fb.p.y - fa.p.y, d2 = fb.p.z - fa.p.z;
+    for(int i = 0; i < 3; i++) vel[i] = Ra[0 + i] * d0 + Ra[3 + i] * d1 + Ra[6 + i] * d2;
+    for(int i = 0; i < 3; i++)
+        for(int j = 0; j < 3; j++) M[i * 3 + j] = Ra[0 + i] * Rb[0 + j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+    double ax = M[7] - M[5], ay = M[2] - M[6], az = M[3] - M[1];
+    double sa = BIOIK_SQRT(ax * ax + ay * ay + az * az) * 0.5;
+    double ca = (M[0] + M[4] + M[8] - 1.0) * 0.5;
+    double angle = BIOIK_ATAN2(sa, ca);
+    if(sa > 1e-12)
+    {
+        double f = angle / (2.0 * sa);
+        rot[0] = ax * f; rot[1] = ay * f; rot[2] = az * f;
+    }
+    else if(ca > 0)
+    {
+        rot[0] = ax * 0.5; rot[1] = ay * 0.5; rot[2] = az * 0.5;
+    }
+    else
+    {
+        rot[0] = angle; rot[1] = 0; rot[2] = 0;
+    }
+}
+BIOIK_HD bool all_below(const double* v, double eps) { return BIOIK_FABS(v[0]) < eps && BIOIK_FABS(v[1]) < eps && BIOIK_FABS(v[2]) < eps; }
+BIOIK_HD double angle_shortest_path(const Q4& a, const Q4& b)
+{
+    double s = BIOIK_SQRT(qlen2(a.x, a.y, a.z, a.w) * qlen2(b.x, b.y, b.z, b.w));
+    double d = a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+    if(d < 0) return BIOIK_ACOS((a.x * -b.x + a.y * -b.y + a.z * -b.z + a.w * -b.w) / s) * 2.0;
+    return BIOIK_ACOS(d / s) * 2.0;
+}
+BIOIK_HD bool check_solution(const DProblem& P, const double* gp, const double* tips, const double* x, const double* seed)
+{
+    for(int gi = 0; gi < P.G; gi++)
+    {
+        const DGoal& g = P.goals[gi];
+        if(g.secondary) continue;
+        const double* p = gp + gi * GOAL_NPARAM;
+        F7 fb = load_frame(tips + 7 * g.tip);
+        F7 fa;
+        fa.p = V3{0, 0, 0};
+        fa.q = Q4{0, 0, 0, 1};
+        double vel[3], rot[3];
+        if(g.type == G_POSITION)
+        {
+            fa.p = V3{p[0], p[1], p[2]};
+            if(P.dpos != DBLMAX)
+            {
+                double pd = BIOIK_SQRT(len2(fb.p.x - fa.p.x, fb.p.y - fa.p.y, fb.p.z - fa.p.z));
+                if(!(pd <= P.dpos)) return false;
+            }
+            if(P.dtwist != DBLMAX)
+            {
+                kdl_twist(fa, fb, vel, rot);
+                if(!all_below(vel, P.dtwist)) return false;
+            }
+        }
+        else if(g.type == G_ORIENTATION)
+        {
+            fa.q = Q4{p[3], p[4], p[5], p[6]};
+            if(P.drot != DBLMAX)
+            {
+                double rd = angle_shortest_path(fb.q, fa.q) * 180 / 3.14159265358979323846;
+                if(!(rd <= P.drot)) return false;
+            }
+            if(P.dtwist != DBLMAX)
+            {
+                kdl_twist(fa, fb, vel, rot);
+                if(!all_below(rot, P.dtwist)) return false;
+            }
+        }
+        else if(g.type == G_POSE)
+        {
+            fa.p = V3{p[0], p[1], p[2]};
+            fa.q = Q4{p[3], p[4], p[5], p[6]};
+            if(P.dpos != DBLMAX || P.drot != DBLMAX)
+            {
+                double pd = BIOIK_SQRT(len2(fb.p.x - fa.p.x, fb.p.y - fa.p.y, fb.p.z - fa.p.z));
+                double rd = angle_shortest_path(fb.q, fa.q) * 180 / 3.14159265358979323846;
+                if(!(pd <= P.dpos)) return false;
+                if(!(rd <= P.drot)) return false;
+            }
+            if(P.dtwist != DBLMAX)
+            {
+                kdl_twist(fa, fb, vel, rot);
+                if(!all_below(vel, P.dtwist) || !all_below(rot, P.dtwist)) return false;
+            }
+        }
+        else
+        {
+            double dmax = BIOIK_FMIN(BIOIK_FMIN(DBLMAX, P.dpos), P.dtwist);
+            double d = goal_value(P, g, p, tips, x, seed) * g.weight_sq;
+            if(!(d < dmax * dmax)) return false;
+        }
+    }
+    return true;
+}
+
+} // namespace bioik

@@ -1,0 +1,203 @@
+// hostsim.cpp — TEST-ONLY host simulation of the CUDA kernels (there is no GPU in the build
+// container).  Compiles bio_ik_b200/csrc/bioik_kernels.cuh unchanged with g++ by shimming the few
+// CUDA constructs it uses: thread-per-item kernels run as plain loops, the warp-cooperative
+// k_evolve runs on 32 OS threads with barrier-based __syncwarp/__shfl emulation.  This lets the
+// CPU test-suite check kernel logic + host flattening bit-for-bit against the oracle before any
+// GPU time is spent.  It is NOT part of libbioik_b200.so and is never used as a fallback.
+#define BIOIK_HOSTSIM 1
+
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+// ---- CUDA shims ---------------------------------------------------------------------------
+struct sim_uint3
+{
+    unsigned x = 0, y = 0, z = 0;
+};
+static thread_local sim_uint3 threadIdx, blockIdx;
+static sim_uint3 blockDim, gridDim;
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(x)
+#define __restrict__
+#define __shared__
+namespace bioik { double smem[1 << 16]; } // the `extern __shared__ double smem[]` of k_evolve
+
+static std::barrier<>* g_warp_barrier = nullptr;
+static uint64_t g_shfl_slots[32];
+static inline void __syncwarp() { g_warp_barrier->arrive_and_wait(); }
+template <class T> static inline T sim_shfl(T v, int src)
+{
+    static_assert(sizeof(T) <= 8, "");
+    uint64_t raw = 0;
+    memcpy(&raw, &v, sizeof(T));
+    g_shfl_slots[threadIdx.x & 31] = raw;
+    g_warp_barrier->arrive_and_wait();
+    uint64_t got = g_shfl_slots[src & 31];
+    g_warp_barrier->arrive_and_wait();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return sim_shfl(v, (int)(threadIdx.x & 31) ^ o); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return sim_shfl(v, src); }
+static inline long long __double_as_longlong(double d)
+{
+    long long r;
+    memcpy(&r, &d, 8);
+    return r;
+}
+using std::fabs;
+
+#include "../../bio_ik_b200/csrc/bioik_host.hpp"
+#include "../../bio_ik_b200/csrc/bioik_kernels.cuh"
+
+using namespace bioik;
+
+namespace
+{
+template <class F> void launch_serial(int blocks, int tpb, F f)
+{
+    blockDim.x = tpb;
+    gridDim.x = blocks;
+    for(int b = 0; b < blocks; b++)
+        for(int t = 0; t < tpb; t++)
+        {
+            blockIdx.x = b;
+            threadIdx.x = t;
+            f();
+        }
+}
+template <class F> void launch_warp(int blocks, F f)
+{
+    blockDim.x = 32;
+    gridDim.x = blocks;
+    std::barrier<> bar(32);
+    g_warp_barrier = &bar;
+    std::vector<std::thread> lanes;
+    for(int l = 0; l < 32; l++)
+        lanes.emplace_back([&, l]() {
+            for(int b = 0; b < blocks; b++)
+            {
+                blockIdx.x = b;
+                threadIdx.x = l;
+                f();
+                bar.arrive_and_wait();
+            }
+        });
+    for(auto& t : lanes) t.join();
+    g_warp_barrier = nullptr;
+}
+
+struct SimTables
+{
+    std::vector<double> uniform, gauss;
+};
+std::map<uint32_t, std::unique_ptr<SimTables>> g_tables;
+std::string g_err;
+} // namespace
+
+extern "C" {
+const char* hostsim_last_error() { return g_err.c_str(); }
+
+const double* hostsim_tables(uint32_t seed, int which)
+{
+    auto& t = g_tables[seed];
+    if(!t)
+    {
+        t.reset(new SimTables());
+        make_tables(seed, t->uniform, t->gauss);
+    }
+    return which ? t->gauss.data() : t->uniform.data();
+}
+
+// device-side RNG helpers, for direct comparison with libstdc++
+void hostsim_minstd_uniform(uint32_t seed, int n, double* out)
+{
+    uint32_t s = seed % 2147483647u;
+    if(s == 0) s = 1;
+    for(int i = 0; i < n; i++) out[i] = minstd_uniform01(s);
+}
+void hostsim_minstd_index(uint32_t seed, uint32_t m, int n, uint64_t* out)
+{
+    uint32_t s = seed % 2147483647u;
+    if(s == 0) s = 1;
+    for(int i = 0; i < n; i++) out[i] = minstd_index(s, m);
+}
+void hostsim_sincos(int n, const double* x, double* s, double* c)
+{
+    for(int i = 0; i < n; i++) d_sincos(x[i], s[i], c[i]);
+}
+
+// the launch sequence of enqueue_solve() in bioik_capi.cu, on host memory
+int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit, double* out_solutions,
+                  double* out_fitness, int32_t* out_success, int32_t* out_steps, double* out_genes, double* out_gradients, double* out_species_fitness)
+{
+    HostRobot R;
+    int rc = intake_robot(robot, R, g_err);
+    if(rc) return rc;
+    static DProblem P; // large
+    rc = build_problem(R, problem, P, g_err);
+    if(rc) return rc;
+    std::vector<int32_t> go;
+    std::vector<uint8_t> re;
+    make_schedules(std::max(steps, 1), cfg->generations, cfg->population, P.n, go, re);
+    size_t n = P.n, T = P.T, gens = cfg->generations;
+    std::vector<double> genes(B * 4 * n), grads(B * 4 * n), sfit(B * 2), sol(B * n), solfit(B), base(B * 2 * n), tip0(B * 2 * T * 7), delta(B * 2 * T * n * 7);
+    std::vector<int32_t> impr(B * 2), done(B), stp(B), succ(B), cc(B * 2 * gens);
+    std::vector<uint32_t> rng(B);
+    std::vector<double> gp_default;
+    if(!goal_params)
+    {
+        gp_default.resize((size_t)B * P.G * GOAL_NPARAM);
+        for(int b = 0; b < B; b++)
+            for(int g = 0; g < P.G; g++)
+                for(int k = 0; k < GOAL_NPARAM; k++) gp_default[((size_t)b * P.G + g) * GOAL_NPARAM + k] = problem->goals[g].p[k];
+        goal_params = gp_default.data();
+    }
+    DState S;
+    memset(&S, 0, sizeof(S));
+    S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit;
+    S.goal_params = goal_params, S.seeds = seeds, S.rng_seeds = rng_seeds;
+    S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
+    S.success = succ.data(), S.ccount = cc.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
+    S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
+    const int TPB = 128;
+    int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
+    launch_serial(qblocks, TPB, [&]() { k_init(&P, S); });
+    for(int step = 0; step < steps; step++)
+    {
+        launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S); });
+        launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
+        if(S.memetic) launch_serial(tblocks, TPB, [&]() { k_memetic(&P, S, step); });
+        launch_serial(qblocks, TPB, [&]() { k_species(&P, S, step); });
+    }
+    launch_serial(qblocks, TPB, [&]() { k_finalize(&P, S, out_solutions, out_fitness, out_success, out_steps); });
+    if(out_genes) memcpy(out_genes, genes.data(), genes.size() * 8);
+    if(out_gradients) memcpy(out_gradients, grads.data(), grads.size() * 8);
+    if(out_species_fitness) memcpy(out_species_fitness, sfit.data(), sfit.size() * 8);
+    return 0;
+}
+
+int hostsim_fk(const BioikRobot* robot, const BioikProblem* problem, int B, const double* variables, double* out_tips, double* out_delta)
+{
+    HostRobot R;
+    int rc = intake_robot(robot, R, g_err);
+    if(rc) return rc;
+    static DProblem P;
+    rc = build_problem(R, problem, P, g_err);
+    if(rc) return rc;
+    if(out_tips) launch_serial((B + 127) / 128, 128, [&]() { k_fk_batch(&P, B, variables, out_tips); });
+    if(out_delta) launch_serial((B + 127) / 128, 128, [&]() { k_approx_batch(&P, B, variables, out_delta); });
+    return 0;
+}
+}

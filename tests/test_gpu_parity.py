@@ -1,0 +1,232 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI, on a real B200 (-m gpu).
+Bar: BIT-IDENTICAL joint angles and fitness (far inside BASELINE.json's 1e-5), because oracle and
+kernels share one arithmetic contract.  The only tolerance-based comparisons are the
+libm-class functions of the success test."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import gpu_util
+import oracle_lib
+from bio_ik_b200 import _abi, goals as G, robots, workloads
+from bio_ik_b200.problem import Problem
+from bio_ik_b200.solver import BioIKError, IKSolver
+
+pytestmark = pytest.mark.gpu
+
+
+def ofk(oracle):
+    return lambda rm, pr, v: oracle.fk(rm, pr, v)
+
+
+# ---------------------------------------------------------------------------------------------
+# rows a9-a11, a6, a7 of SURVEY.md §8(a): exact FK, Jacobian/approximator, approximate fitness
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("maker,group", [(robots.pr2_like, "all"), (robots.pr2_like, "right_arm"), (robots.snake, "all"), (robots.shadow_like_hand, "hand"),
+                                         (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all")])
+def test_exact_fk_and_delta_frames(oracle, maker, group):
+    rm, groups = maker()
+    g = groups[group]
+    pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
+    solver = IKSolver(rm).initialize(pr)
+    rng = np.random.default_rng(3)
+    v = workloads.sample_configurations(rm, range(rm.n_vars), 500, rng)
+    v[:8] *= 50.0  # far outside the limits: exercises the large-argument path of the contract sin/cos
+    assert np.array_equal(solver.fk(v), oracle.fk(rm, pr, v))
+    d, mask = oracle.approx(rm, pr, v[:200])
+    d = d.copy()
+    d[mask == 0, 6] = 0.0
+    assert np.array_equal(solver.approx(v[:200]), d)
+
+
+def test_approximate_fitness_all_device_goals(oracle):
+    rm, groups = robots.pr2_like()
+    g = groups["all"]
+    r, l = "r_wrist_roll_link", "l_wrist_roll_link"
+    gl = [G.PoseGoal(r, (0.6, -0.2, 0.9), (0.1, 0.2, 0.3, 0.9)), G.PositionGoal(l, (0.5, 0.3, 1.0), 0.7), G.OrientationGoal(l, (0, 0.5, 0, 1), 1.3),
+          G.LookAtGoal(r, (1, 0, 0), (2, 0.5, 1)), G.MaxDistanceGoal(l, (0.5, 0, 1), 0.3), G.MinDistanceGoal(r, (0.5, 0, 1), 0.6), G.LineGoal(r, (0.5, 0, 1), (1, 1, 0)),
+          G.PlaneGoal(l, (0.5, 0, 1), (0, 1, 1)), G.SideGoal(r, (0, 0, 1), (0, 1, 0)), G.DirectionGoal(l, (1, 0, 0), (0, 0, 1)), G.JointVariableGoal("torso_lift_joint", 0.2, 2.0),
+          G.AvoidJointLimitsGoal(1.5), G.CenterJointsGoal(0.5, secondary=False), G.RegularizationGoal(0.25), G.MinimalDisplacementGoal(2.0)]
+    pr = Problem().initialize(rm, g, gl)
+    solver = IKSolver(rm).initialize(pr)
+    rng = np.random.default_rng(4)
+    B, M, n = 40, 16, len(pr.active_variables)
+    base = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    genes = base[:, pr.active_variables][:, None, :] + rng.normal(0, 0.2, (B, M, n))
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    gp[:, 0, 0:3] += rng.normal(0, 0.1, (B, 3))
+    p_ref, s_ref = oracle.approx_fitness(rm, pr, gp, seeds, base, genes)
+    p_gpu, s_gpu = solver.approx_fitness(gp, seeds, base, genes)
+    assert np.array_equal(p_gpu, p_ref) and np.array_equal(s_gpu, s_ref)
+    # NULL goal_params -> BioikGoal::p defaults
+    p_ref, s_ref = oracle.approx_fitness(rm, pr, None, seeds, base, genes)
+    p_gpu, s_gpu = solver.approx_fitness(None, seeds, base, genes)
+    assert np.array_equal(p_gpu, p_ref) and np.array_equal(s_gpu, s_ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole step(): trajectory-level parity (rows a1-a8, a12-a15)
+# ---------------------------------------------------------------------------------------------
+TRACE_CASES = [
+    ("cfg2", 16, 18, "q", 8, 10), ("cfg2", 16, 64, "q", 8, 25), ("cfg2", 24, 128, "q", 8, 25), ("cfg2", 8, 35, "q", 8, 7), ("cfg2", 8, 4, "q", 8, 5), ("cfg2", 4, 256, "q", 8, 3),
+    ("cfg2", 16, 18, 0, 16, 10), ("cfg2", 16, 40, "l", 8, 10), ("cfg3", 12, 128, "q", 8, 12), ("cfg4", 8, 128, "q", 8, 10), ("cfg4", 8, 37, "l", 8, 6), ("cfg5", 12, 128, "q", 8, 10),
+]
+
+
+@pytest.mark.parametrize("name,B,pop,mode,gens,steps", TRACE_CASES)
+def test_solver_state_is_bit_identical_to_the_oracle(oracle, name, B, pop, mode, gens, steps):
+    w = workloads.make(name, ofk(oracle), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=gens)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    solver = gpu_util.make_solver(w, pop, mode, gens)
+    got = solver.trace(w.goal_params, w.seeds, w.rng_seeds, steps)
+    gpu_util.assert_bit_equal(got, ref, what=f"{name} pop={pop}")
+    res = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, steps)
+    gpu_util.assert_bit_equal(res, ref, keys=("solutions", "fitness", "success", "steps"), what=f"{name} pop={pop}")
+
+
+def test_table_seed_and_query_seed_are_honoured(oracle):
+    w = workloads.make("cfg2", ofk(oracle), batch=8)
+    cfg = oracle_lib.make_cfg(population=18, table_seed=77)
+    rs = np.array([5, 5, 9, 1 << 31, 0, 2147483647, 3, 3], dtype=np.uint32)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, rs, 8)
+    solver = gpu_util.make_solver(w, 18, random_seed=77)
+    gpu_util.assert_bit_equal(solver.trace(w.goal_params, w.seeds, rs, 8), ref)
+
+
+def test_early_exit_matches_the_driver_contract(oracle):
+    w = workloads.make("cfg2", ofk(oracle), batch=64)
+    cfg = oracle_lib.make_cfg(population=32)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 22, early_exit=True)
+    solver = gpu_util.make_solver(w, 32)
+    got = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 22, early_exit=True)
+    gpu_util.assert_bit_equal(got, ref, keys=("solutions", "fitness", "success", "steps"))
+    assert set(got["steps"].tolist()) <= {4, 8, 12, 16, 20, 22} and got["steps"].min() < 22
+
+
+def test_batch_composition_does_not_matter(oracle):
+    """Queries are independent: a query's answer does not depend on its batch neighbours or position."""
+    w = workloads.make("cfg2", ofk(oracle), batch=300)
+    solver = gpu_util.make_solver(w, 64)
+    full = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 9)
+    idx = np.array([299, 0, 17, 150, 151, 33, 32, 31])
+    part = solver.solve_batch(w.goal_params[idx], w.seeds[idx], w.rng_seeds[idx], 9)
+    for k in ("solutions", "fitness", "success"):
+        assert np.array_equal(part[k], full[k][idx])
+    one = solver.solve_batch(w.goal_params[5:6], w.seeds[5:6], w.rng_seeds[5:6], 9)
+    assert np.array_equal(one["solutions"][0], full["solutions"][5])
+
+
+def test_zero_steps_returns_the_seed(oracle):
+    w = workloads.make("cfg2", ofk(oracle), batch=5)
+    solver = gpu_util.make_solver(w, 18)
+    res = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 0)
+    assert np.array_equal(res["solutions"], w.seeds) and np.all(res["steps"] == 0)
+    cfg = oracle_lib.make_cfg(population=18)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 0)
+    assert np.array_equal(res["fitness"], ref["fitness"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties + a bounded oracle sample
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_full_size_10k_queries(oracle):
+    w = workloads.make("cfg2", ofk(oracle), batch=10000)
+    solver = gpu_util.make_solver(w, 128)
+    res = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 25)
+    again = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 25)
+    for k in res:
+        assert np.array_equal(res[k], again[k])  # deterministic
+    assert res["success"].mean() >= 0.93
+    ok = res["success"] == 1
+    # FK -> IK -> FK round trip: solved queries reach their goal pose (dtwist = 1e-5 on every twist component)
+    tips = solver.fk(res["solutions"])
+    assert np.abs(tips[ok, 0, :3] - w.goal_params[ok, 0, :3]).max() < 2e-5
+    qerr = np.minimum(np.abs(tips[ok, 0, 3:] - w.goal_params[ok, 0, 3:7]).max(1), np.abs(tips[ok, 0, 3:] + w.goal_params[ok, 0, 3:7]).max(1))
+    assert qerr.max() < 2e-5
+    # the reported fitness IS the goal error of the returned solution (idempotent re-evaluation)
+    p = w.goal_params[:, 0]
+    e = ((p[:, :3] - tips[:, 0, :3]) ** 2).sum(1) + np.minimum(((p[:, 3:7] - tips[:, 0, 3:]) ** 2).sum(1), ((p[:, 3:7] + tips[:, 0, 3:]) ** 2).sum(1)) * 0.25
+    assert np.allclose(res["fitness"], e, rtol=1e-9, atol=1e-30)
+    # clip limits hold
+    a = w.robot.arrays
+    for ivar in w.problem.active_variables:
+        if a["var_bounded"][ivar] and a["var_max"][ivar] - a["var_min"][ivar] < 6.28:
+            assert res["solutions"][:, ivar].min() >= a["var_min"][ivar] and res["solutions"][:, ivar].max() <= a["var_max"][ivar]
+    # inactive variables pass through
+    inactive = [v for v in range(w.robot.n_vars) if v not in w.problem.active_variables]
+    assert np.array_equal(res["solutions"][:, inactive], w.seeds[:, inactive])
+    # bounded oracle sample of the same batch: bit-identical
+    idx = np.r_[0:96, 9990:10000]
+    cfg = oracle_lib.make_cfg(population=128)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params[idx], w.seeds[idx], w.rng_seeds[idx], 25)
+    for k in ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(res[k][idx], ref[k]), k
+
+
+@pytest.mark.parametrize("name,B,sample", [("cfg3", 4096, 24), ("cfg4", 2048, 16), ("cfg5", 8192, 16)])
+def test_other_configs_full_size(oracle, name, B, sample):
+    w = workloads.make(name, ofk(oracle), batch=B)
+    solver = gpu_util.make_solver(w, 128)
+    res = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 25)
+    assert np.all(np.isfinite(res["fitness"])) and np.all(res["steps"] == 25)
+    assert np.median(res["fitness"]) < 1e-6
+    idx = np.arange(sample)
+    cfg = oracle_lib.make_cfg(population=128)
+    ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params[idx], w.seeds[idx], w.rng_seeds[idx], 25)
+    for k in ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(res[k][idx], ref[k]), k
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour of the boundary (status codes instead of ERROR(...) exceptions)
+# ---------------------------------------------------------------------------------------------
+def test_error_paths():
+    rm, groups = robots.pr2_like()
+    g = groups["right_arm"]
+    pr = Problem().initialize(rm, g, [G.PoseGoal("r_wrist_roll_link")])
+    solver = IKSolver(rm)
+    with pytest.raises(BioIKError) as e:
+        solver.solve_batch(None, np.zeros((1, rm.n_vars)), np.ones(1, dtype=np.uint32), 1)
+    assert e.value.code == _abi.E_NO_PROBLEM
+    p = pr.to_abi()
+    p.goals[0].type = 99
+    assert solver.lib.bioik_set_problem(solver._ctx, C.byref(p)) == _abi.E_UNSUPPORTED_GOAL
+    p.goals[0].type = _abi.GOAL_POSE
+    assert solver.lib.bioik_set_problem(solver._ctx, C.byref(p)) == _abi.OK
+    with pytest.raises(BioIKError) as e:
+        IKSolver(rm, population=3)
+    assert e.value.code == _abi.E_LIMIT
+    with pytest.raises(BioIKError):
+        IKSolver(rm, mode="bio1")
+    # a floating joint on the chain is refused, not silently mis-solved
+    links = [robots.Link("world", None), robots.Link("base", "world", _abi.JOINT_FLOATING, joint_name="virtual"), robots.Link("arm", "base", _abi.JOINT_REVOLUTE, lower=-1, upper=1, joint_name="j")]
+    rm2 = robots.RobotModel("floating", links)
+    g2 = robots.JointModelGroup(rm2, "all", ["virtual", "j"], ["arm"])
+    pr2 = Problem().initialize(rm2, g2, [G.PositionGoal("arm")])
+    with pytest.raises(BioIKError) as e:
+        IKSolver(rm2).initialize(pr2)
+    assert e.value.code == _abi.E_UNSUPPORTED_JOINT
+
+
+def test_device_pointer_entry_point(oracle):
+    torch = pytest.importorskip("torch")
+    w = workloads.make("cfg2", ofk(oracle), batch=128)
+    solver = gpu_util.make_solver(w, 64)
+    dev = torch.device("cuda:0")
+    gp = torch.from_numpy(w.goal_params).to(dev)
+    seeds = torch.from_numpy(w.seeds).to(dev)
+    rs = torch.from_numpy(w.rng_seeds.astype(np.int64)).to(dev).to(torch.int32)  # same 32-bit pattern
+    sol = torch.empty((128, w.robot.n_vars), dtype=torch.float64, device=dev)
+    fit = torch.empty(128, dtype=torch.float64, device=dev)
+    succ = torch.empty(128, dtype=torch.int32, device=dev)
+    stp = torch.empty(128, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    solver.solve_batch_device(128, gp.data_ptr(), seeds.data_ptr(), rs.data_ptr(), 6, False, sol.data_ptr(), fit.data_ptr(), succ.data_ptr(), stp.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    ref = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)
+    assert np.array_equal(sol.cpu().numpy(), ref["solutions"]) and np.array_equal(fit.cpu().numpy(), ref["fitness"])
+    ev, nev, se, nse = solver.kernel_time()
+    assert nev >= 12 and ev > 0 and solver.launch_count() > 0

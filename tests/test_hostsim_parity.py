@@ -1,0 +1,78 @@
+"""CPU check of the CUDA kernel SOURCE before any GPU time is spent: tests/hostsim compiles
+bioik_kernels.cuh + bioik_host.hpp with g++ (CUDA constructs shimmed, the warp kernel on 32 OS
+threads) and must agree BIT-FOR-BIT with the oracle.  Test infrastructure only."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hostsim_lib
+import oracle_lib
+from bio_ik_b200 import _abi, workloads
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return hostsim_lib.HostSim()
+
+
+def test_host_table_generation_equals_oracle_tables(sim, oracle):
+    u, g = oracle.table_arrays(7)
+    su = np.ctypeslib.as_array(sim.lib.hostsim_tables(7, 0), shape=(1 << 23,))
+    sg = np.ctypeslib.as_array(sim.lib.hostsim_tables(7, 1), shape=(1 << 23,))
+    assert np.array_equal(u, su) and np.array_equal(g, sg)
+
+
+def test_device_minstd_matches_libstdcpp(sim, oracle):
+    for seed in (1, 2, 12345, 2147483647, 0, 4000000000):
+        a, b = np.zeros(64), np.zeros(64)
+        oracle.lib.oracle_minstd_uniform(seed, 64, _abi.dptr(a))
+        sim.lib.hostsim_minstd_uniform(seed, 64, _abi.dptr(b))
+        assert np.array_equal(a, b)
+        for m in (1, 2, 15, 125, 253, 1 << 20):
+            x, y = (C.c_uint64 * 64)(), (C.c_uint64 * 64)()
+            oracle.lib.oracle_minstd_index(seed, m, 64, x)
+            sim.lib.hostsim_minstd_index(seed, m, 64, y)
+            assert list(x) == list(y)
+
+
+def test_device_sincos_is_the_oracle_sincos(sim, oracle):
+    x = np.concatenate([np.random.default_rng(0).uniform(-50, 50, 20000), [0.0, 1e5, 1.00001e5, -3e8, 1e300]])
+    s, c = oracle.sincos(x)
+    s2, c2 = np.empty_like(x), np.empty_like(x)
+    sim.lib.hostsim_sincos(len(x), _abi.dptr(x), _abi.dptr(s2), _abi.dptr(c2))
+    assert np.array_equal(s, s2) and np.array_equal(c, c2)
+
+
+CASES = [("cfg2", 4, 18, "q", 8, 6), ("cfg2", 2, 128, "q", 8, 3), ("cfg2", 3, 21, 0, 16, 3), ("cfg2", 3, 33, "l", 8, 4), ("cfg3", 2, 40, "q", 8, 3), ("cfg4", 2, 40, "q", 8, 3),
+         ("cfg5", 2, 36, "q", 8, 2)]
+
+
+@pytest.mark.parametrize("name,B,pop,mode,gens,steps", CASES)
+def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B, pop, mode, gens, steps):
+    w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=gens)
+    a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_simulated_fk_and_delta_frames(sim, oracle):
+    w = workloads.make("cfg3", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=6)
+    tips, delta = sim.fk(w.robot, w.problem, w.targets, delta=True)
+    assert np.array_equal(tips, oracle.fk(w.robot, w.problem, w.targets))
+    d, mask = oracle.approx(w.robot, w.problem, w.targets)
+    d = d.copy()
+    d[mask == 0, 6] = 0.0  # device convention: unmasked delta frames are all-zero
+    assert np.array_equal(delta, d)
+
+
+def test_early_exit_contract(sim, oracle):
+    w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=6)
+    cfg = oracle_lib.make_cfg(population=24)
+    a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 14, early_exit=True)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 14, early_exit=True)
+    for k in ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(a[k], b[k]), k
+    assert set(b["steps"].tolist()) <= {4, 8, 12, 14}
