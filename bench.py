@@ -90,11 +90,13 @@ def cpu_port_rate(args, w_small, seconds, variant="fast"):
     t0 = time.perf_counter()
     o.solve(w_small.robot, w_small.problem, cfg, w_small.goal_params[:n0], w_small.seeds[:n0], w_small.rng_seeds[:n0], args.solver_steps, nthreads=threads)
     dt0 = time.perf_counter() - t0
-    n1 = int(min(len(w_small.seeds), max(n0, seconds / max(dt0, 1e-6) * n0)))
+    n1 = int(max(n0, seconds / max(dt0, 1e-6) * n0))
+    reps = -(-n1 // len(w_small.seeds))
+    gp, sd, rs = (np.concatenate([a] * reps)[:n1] for a in (w_small.goal_params, w_small.seeds, w_small.rng_seeds))
     t0 = time.perf_counter()
-    o.solve(w_small.robot, w_small.problem, cfg, w_small.goal_params[:n1], w_small.seeds[:n1], w_small.rng_seeds[:n1], args.solver_steps, nthreads=threads)
+    o.solve(w_small.robot, w_small.problem, cfg, gp, sd, rs, args.solver_steps, nthreads=threads)
     dt = time.perf_counter() - t0
-    return n1 / dt, threads, f"first {n1} queries of the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {dt:.1f} s"
+    return n1 / dt, threads, f"{n1} queries drawn from the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {threads} threads, {dt:.1f} s"
 
 
 def run_reference(args):
@@ -108,7 +110,7 @@ def run_reference(args):
     o = oracle_lib.Oracle("strict")
     w, cid = make_workload(args, None)
     threads = os.cpu_count() or 1
-    sample = int(min(args.batch, max(64, 48 * threads)))
+    sample = int(min(args.batch, max(256, 256 * threads)))
     w.generate(lambda rm, pr, v: o.fk(rm, pr, v), B=sample, cfg_id=cid, seed_noise=(0.1 if args.config == "cfg4" else None))
     fast = oracle_lib.Oracle("fast")
     cfg = oracle_lib.make_cfg(population=args.population)
@@ -176,7 +178,8 @@ def main():
     d_steps = torch.empty(B, dtype=torch.int32, device=dev)
     gathered = torch.empty((world * B, n_vars + 3), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # the solve, the L2 flush, the events and NCCL all run on this stream
+    torch.cuda.set_stream(stream)
 
     def one_pass(k):
         g, s, r = d_batches[k % n_batches]
@@ -284,7 +287,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         wcpu, _ = make_workload(args, None)
-        nb = min(B, 4096)
+        nb = B
         wcpu.goal_params, wcpu.seeds, wcpu.rng_seeds = batches[0][0][:nb], batches[0][1][:nb], batches[0][2][:nb]
         rate, threads, desc = cpu_port_rate(args, wcpu, args.cpu_seconds)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}

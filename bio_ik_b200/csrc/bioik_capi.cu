@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
@@ -48,6 +49,8 @@ struct bioik_ctx
     int sched_steps = -1, sched_n = -1;
     int32_t* d_gauss_off = nullptr;
     uint8_t* d_rate_exp = nullptr;
+    double* d_mtab = nullptr; // [calls][n][C] mutation table of the fast generation kernel
+    bool force_generic = false; // BIOIK_FORCE_GENERIC=1: always use the generic generation kernel (tests)
 
     // state
     int capB = 0;
@@ -158,18 +161,31 @@ int ensure_staging(bioik_ctx* ctx, int B)
     return BIOIK_OK;
 }
 
+int check_launch(bioik_ctx* ctx, const char* what);
+
 int ensure_schedules(bioik_ctx* ctx, int steps)
 {
     if(ctx->sched_steps >= steps && ctx->sched_n == ctx->hP.n) return BIOIK_OK;
     std::vector<int32_t> go;
     std::vector<uint8_t> re;
     make_schedules(steps, ctx->cfg.generations, ctx->cfg.population, ctx->hP.n, go, re);
-    cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp);
-    ctx->d_gauss_off = nullptr, ctx->d_rate_exp = nullptr;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab);
+    ctx->d_gauss_off = nullptr, ctx->d_rate_exp = nullptr, ctx->d_mtab = nullptr;
     CU(ctx, cudaMalloc(&ctx->d_gauss_off, go.size() * 4));
     CU(ctx, cudaMalloc(&ctx->d_rate_exp, re.size()));
     CU(ctx, cudaMemcpy(ctx->d_gauss_off, go.data(), go.size() * 4, cudaMemcpyHostToDevice));
     CU(ctx, cudaMemcpy(ctx->d_rate_exp, re.data(), re.size(), cudaMemcpyHostToDevice));
+    {
+        // query-independent mutation table of the fast generation kernel (bioik_evolve_fast.cuh)
+        const int calls = (int)go.size(), C = ctx->cfg.population;
+        const long long total = (long long)calls * ctx->hP.n * C;
+        CU(ctx, cudaMalloc(&ctx->d_mtab, (size_t)total * 8));
+        k_mutation_table<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, calls, C, ctx->d_gauss, ctx->d_gauss_off, ctx->d_rate_exp, ctx->d_mtab);
+        int rc = check_launch(ctx, "k_mutation_table");
+        if(rc != BIOIK_OK) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     ctx->sched_steps = steps;
     ctx->sched_n = ctx->hP.n;
     return BIOIK_OK;
@@ -241,10 +257,21 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
 
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    EvolveSmem L{P.n, P.T, P.G};
     const int warps_per_block = 4;
-    size_t smem = (size_t)warps_per_block * L.total() * sizeof(double);
-    if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P.T, S.C, P.n_joint_goals);
+    size_t smem;
+    if(fast)
+    {
+        FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0};
+        smem = (size_t)warps_per_block * L.total() * sizeof(double);
+        if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    else
+    {
+        EvolveSmem L{P.n, P.T, P.G};
+        smem = (size_t)warps_per_block * L.total() * sizeof(double);
+        if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int eblocks = (2 * B + warps_per_block - 1) / warps_per_block;
 
     k_init<<<qblocks, TPB, 0, st>>>(ctx->dP, S);
@@ -259,7 +286,10 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         ctx->pending.push_back(s1);
         EventPair ev = get_pair(ctx, 0);
         cudaEventRecord(ev.a, st);
-        k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
+        if(fast)
+            fast<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step, ctx->d_mtab);
+        else
+            k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
         if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
         cudaEventRecord(ev.b, st);
         ctx->pending.push_back(ev);
@@ -344,6 +374,10 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         return fail(nullptr, BIOIK_E_CUDA, msg);
     }
     memset(&ctx->S, 0, sizeof(ctx->S));
+    {
+        const char* fg = getenv("BIOIK_FORCE_GENERIC");
+        ctx->force_generic = fg && fg[0] == '1';
+    }
     *out = ctx;
     return BIOIK_OK;
 }
@@ -355,7 +389,7 @@ void bioik_destroy(bioik_ctx* ctx)
     if(ctx->stream) cudaStreamSynchronize(ctx->stream);
     for(auto& p : ctx->pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
-    cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->state_block);
+    cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -75,7 +75,7 @@ struct DGene // one active variable (problem.active_variables order)
     int32_t var;       // robot variable index
     int32_t dep_start; // range in DProblem::dep_* (joint_dependencies of the variable's joint, :570-587)
     int32_t dep_count; // 0 if the variable's own joint mimics another joint (:623)
-    int32_t pad;
+    int32_t tipmask;   // bit t set: the variable can move tip t (OR of its dependency joints' tipmask)
     double clip_min, clip_max, span, vmin, vmax, vel_weight; // robot_info.h:48-55, problem.cpp:206-225
 };
 struct DGoal
@@ -90,7 +90,7 @@ struct DMimic
 };
 struct DProblem
 {
-    int32_t n_vars, n, T, L, G, n_mimic, has_secondary, pad;
+    int32_t n_vars, n, T, L, G, n_mimic, has_secondary, n_joint_goals;
     double dpos, drot, dtwist;
     int32_t tip_slot[MAX_TIPS];
     int32_t gene_of_var[MAX_VARS]; // -1 if inactive

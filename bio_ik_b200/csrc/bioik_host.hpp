@@ -226,6 +226,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         // dependencies of the variable's joint; none if that joint itself mimics another (:623)
         Gn.dep_start = ndep;
         Gn.dep_count = 0;
+        Gn.tipmask = 0;
         if(j >= 0 && R.mimic[j] < 0)
             for(int jl : deps[j])
             {
@@ -233,6 +234,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
                 for(int m = jl; R.mimic[m] >= 0 && R.mimic[m] != jl; m = R.mimic[m]) scale *= R.mimic_factor[m];
                 P.dep_slot[ndep] = slot_of_link[jl];
                 P.dep_scale[ndep] = scale;
+                Gn.tipmask |= P.slots[slot_of_link[jl]].tipmask;
                 ndep++;
                 Gn.dep_count++;
             }
@@ -257,8 +259,8 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
             if(bg.var < 0 || bg.var >= R.n_vars) return host_fail(err, BIOIK_E_INVALID, "goal variable out of range");
             D.var_index = P.gene_of_var[bg.var] >= 0 ? P.gene_of_var[bg.var] : -1 - bg.var;
         }
-        if(D.secondary)
-            P.has_secondary = 1;
+        if(D.secondary) P.has_secondary = 1;
+        if(bg.type >= BIOIK_GOAL_AVOID_JOINT_LIMITS && bg.type <= BIOIK_GOAL_JOINT_VARIABLE) P.n_joint_goals++;
     }
     // thresholds (src/problem.cpp:90-95)
     P.dpos = p->dpos;

@@ -603,3 +603,5 @@ __global__ void k_approx_fitness(const DProblem* __restrict__ Pp, int B, int M, 
 }
 
 } // namespace bioik
+
+#include "bioik_evolve_fast.cuh"

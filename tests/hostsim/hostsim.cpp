@@ -140,7 +140,7 @@ void hostsim_sincos(int n, const double* x, double* s, double* c)
 
 // the launch sequence of enqueue_solve() in bioik_capi.cu, on host memory
 int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit, double* out_solutions,
-                  double* out_fitness, int32_t* out_success, int32_t* out_steps, double* out_genes, double* out_gradients, double* out_species_fitness)
+                  double* out_fitness, int32_t* out_success, int32_t* out_steps, double* out_genes, double* out_gradients, double* out_species_fitness, int use_fast)
 {
     HostRobot R;
     int rc = intake_robot(robot, R, g_err);
@@ -173,11 +173,28 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
+    EvolveFastKernel fast = use_fast ? select_evolve_fast(P.T, S.C, P.n_joint_goals) : nullptr;
+    if(use_fast && !fast)
+    {
+        g_err = "no fast kernel instantiation for this problem";
+        return BIOIK_E_LIMIT;
+    }
+    std::vector<double> mtab;
+    if(fast)
+    {
+        int calls = (int)go.size();
+        long long total = (long long)calls * P.n * S.C;
+        mtab.resize(total);
+        launch_serial((int)((total + 255) / 256), 256, [&]() { k_mutation_table(&P, calls, S.C, S.gauss, S.gauss_off, S.rate_exp, mtab.data()); });
+    }
     launch_serial(qblocks, TPB, [&]() { k_init(&P, S); });
     for(int step = 0; step < steps; step++)
     {
         launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S); });
-        launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
+        if(fast)
+            launch_warp(2 * B, [&]() { fast(&P, S, step, mtab.data()); });
+        else
+            launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
         if(S.memetic) launch_serial(tblocks, TPB, [&]() { k_memetic(&P, S, step); });
         launch_serial(qblocks, TPB, [&]() { k_species(&P, S, step); });
     }

@@ -22,14 +22,14 @@ class HostSim:
         lib.hostsim_minstd_index.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         lib.hostsim_sincos.argtypes = [C.c_int, dp, dp, dp]
         lib.hostsim_solve.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_int, dp, dp, up, C.c_int, C.c_int,
-                                      dp, dp, ip, ip, dp, dp, dp]
+                                      dp, dp, ip, ip, dp, dp, dp, C.c_int]
         lib.hostsim_fk.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, dp, dp, dp]
 
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError(f"hostsim rc={rc}: " + self.lib.hostsim_last_error().decode())
 
-    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False):
+    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, fast=False):
         seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
         B, n = seeds.shape[0], len(problem.active_variables)
         gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
@@ -39,7 +39,7 @@ class HostSim:
         r, p = robot.to_abi(), problem.to_abi()
         self._check(self.lib.hostsim_solve(C.byref(r), C.byref(p), C.byref(cfg), B, _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit),
                                            _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["steps"]),
-                                           _abi.dptr(res["genes"]), _abi.dptr(res["gradients"]), _abi.dptr(res["species_fitness"])))
+                                           _abi.dptr(res["genes"]), _abi.dptr(res["gradients"]), _abi.dptr(res["species_fitness"]), int(fast)))
         return res
 
     def fk(self, robot, problem, variables, delta=False):

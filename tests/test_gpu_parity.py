@@ -230,3 +230,36 @@ def test_device_pointer_entry_point(oracle):
     assert np.array_equal(sol.cpu().numpy(), ref["solutions"]) and np.array_equal(fit.cpu().numpy(), ref["fitness"])
     ev, nev, se, nse = solver.kernel_time()
     assert nev >= 12 and ev > 0 and solver.launch_count() > 0
+
+
+def test_generic_and_fast_generation_kernels_agree(oracle, monkeypatch):
+    """The generic kernel (k_evolve, any problem shape) and the register-blocked k_evolve_fast are two schedules of
+    the same arithmetic: identical results, both identical to the oracle."""
+    for name, B, pop, steps in (("cfg2", 32, 128, 6), ("cfg3", 16, 100, 4), ("cfg4", 8, 128, 4), ("cfg5", 8, 64, 3)):
+        w = workloads.make(name, ofk(oracle), batch=B)
+        fast = gpu_util.make_solver(w, pop)
+        monkeypatch.setenv("BIOIK_FORCE_GENERIC", "1")
+        generic = gpu_util.make_solver(w, pop)
+        monkeypatch.delenv("BIOIK_FORCE_GENERIC")
+        a = fast.trace(w.goal_params, w.seeds, w.rng_seeds, steps)
+        b = generic.trace(w.goal_params, w.seeds, w.rng_seeds, steps)
+        gpu_util.assert_bit_equal(a, b, what=name + " fast vs generic")
+        cfg = oracle_lib.make_cfg(population=pop)
+        ref = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+        gpu_util.assert_bit_equal(a, ref, what=name)
+
+
+def test_mixed_goal_problem_on_gpu(oracle):
+    rm, groups = robots.pr2_like()
+    g = groups["all"]
+    r, l = "r_wrist_roll_link", "l_wrist_roll_link"
+    gl = [G.PositionGoal(r, (0.6, -0.3, 0.9)), G.LookAtGoal(l, (1, 0, 0), (2, 0.5, 1), 0.3), G.JointVariableGoal("torso_lift_joint", 0.2, 2.0), G.CenterJointsGoal(0.5, secondary=False),
+          G.LineGoal(l, (0.5, 0.2, 1), (1, 1, 0), 0.7), G.MinimalDisplacementGoal(1.5), G.AvoidJointLimitsGoal(0.8), G.DirectionGoal(r, (1, 0, 0), (0, 0, 1), 0.4)]
+    pr = Problem().initialize(rm, g, gl)
+    rng = np.random.default_rng(5)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 40, rng)
+    rs = np.arange(40, dtype=np.uint32) + 3
+    cfg = oracle_lib.make_cfg(population=45)
+    ref = oracle.solve(rm, pr, cfg, None, seeds, rs, 8)
+    solver = IKSolver(rm, population=45).initialize(pr)
+    gpu_util.assert_bit_equal(solver.trace(None, seeds, rs, 8), ref)

@@ -48,12 +48,17 @@ CASES = [("cfg2", 4, 18, "q", 8, 6), ("cfg2", 2, 128, "q", 8, 3), ("cfg2", 3, 21
          ("cfg5", 2, 36, "q", 8, 2)]
 
 
-@pytest.mark.parametrize("name,B,pop,mode,gens,steps", CASES)
-def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B, pop, mode, gens, steps):
+CASES_FAST = CASES + [("cfg2", 2, 64, "q", 8, 3), ("cfg2", 2, 200, "q", 8, 2), ("cfg2", 3, 4, "q", 8, 3), ("cfg3", 2, 128, "q", 8, 2), ("cfg4", 2, 70, "l", 8, 2)]
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name,B,pop,mode,gens,steps", CASES_FAST)
+def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B, pop, mode, gens, steps, fast):
+    """fast=False: generic generation kernel (k_evolve); fast=True: register-blocked k_evolve_fast + mutation table."""
     w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
     cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=gens)
     a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
-    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, fast=fast)
     for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
         assert np.array_equal(a[k], b[k]), k
 
@@ -72,7 +77,28 @@ def test_early_exit_contract(sim, oracle):
     w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=6)
     cfg = oracle_lib.make_cfg(population=24)
     a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 14, early_exit=True)
-    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 14, early_exit=True)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 14, early_exit=True, fast=True)
     for k in ("solutions", "fitness", "success", "steps"):
         assert np.array_equal(a[k], b[k]), k
     assert set(b["steps"].tolist()) <= {4, 8, 12, 14}
+
+
+def test_mixed_goals_fast_kernel(sim, oracle):
+    """link goals of several kinds + primary and secondary joint-space goals + a JointVariableGoal, 2 tips."""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.pr2_like()
+    g = groups["all"]
+    r, l = "r_wrist_roll_link", "l_wrist_roll_link"
+    gl = [G.PositionGoal(r, (0.6, -0.3, 0.9)), G.LookAtGoal(l, (1, 0, 0), (2, 0.5, 1), 0.3), G.JointVariableGoal("torso_lift_joint", 0.2, 2.0), G.CenterJointsGoal(0.5, secondary=False),
+          G.LineGoal(l, (0.5, 0.2, 1), (1, 1, 0), 0.7), G.MinimalDisplacementGoal(1.5), G.AvoidJointLimitsGoal(0.8), G.DirectionGoal(r, (1, 0, 0), (0, 0, 1), 0.4)]
+    pr = Problem().initialize(rm, g, gl)
+    rng = np.random.default_rng(5)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 3, rng)
+    rs = np.array([3, 4, 5], dtype=np.uint32)
+    cfg = oracle_lib.make_cfg(population=45)
+    a = oracle.solve(rm, pr, cfg, None, seeds, rs, 3)
+    for fast in (False, True):
+        b = sim.solve(rm, pr, cfg, None, seeds, rs, 3, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(a[k], b[k]), (k, fast)
