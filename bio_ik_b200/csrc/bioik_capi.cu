@@ -179,7 +179,7 @@ int ensure_schedules(bioik_ctx* ctx, int steps)
     {
         // query-independent mutation table of the fast generation kernel (bioik_evolve_fast.cuh)
         const int calls = (int)go.size(), C = ctx->cfg.population;
-        const long long total = (long long)calls * ctx->hP.n * C;
+        const long long total = (long long)calls * ctx->hP.n * mtab_row(C);
         CU(ctx, cudaMalloc(&ctx->d_mtab, (size_t)total * 8));
         k_mutation_table<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(ctx->dP, calls, C, ctx->d_gauss, ctx->d_gauss_off, ctx->d_rate_exp, ctx->d_mtab);
         int rc = check_launch(ctx, "k_mutation_table");
@@ -258,7 +258,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
     const int warps_per_block = 4;
-    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P.T, S.C, P.n_joint_goals);
+    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C);
     size_t smem;
     if(fast)
     {

@@ -29,25 +29,35 @@ namespace bioik
 
 constexpr int FAST_MAX_JOINT_GOALS = 4;
 
-// mutation table: mtab[(call * n + gene) * C + child] = r * (mutation_rate * span)   (:288-293)
+// row length of the mutation table: child slots 2..C-1 re-indexed j = c - 2 and padded to whole warps
+// to a power of two >= 32 (32, 64, 128 or 256) so that every register-block size divides it
+__host__ __device__ inline int mtab_row(int C)
+{
+    int r = 32;
+    while(r < C - 2) r *= 2;
+    return r;
+}
+
+// mutation table: mtab[(call * n + gene) * mtab_row(C) + j] = r * (mutation_rate * span), j = child - 2   (:288-293)
+// (zero in the padding, so padded lanes read valid memory and their results are simply never selected)
 __global__ void k_mutation_table(const DProblem* __restrict__ Pp, int calls, int C, const double* __restrict__ gauss, const int32_t* __restrict__ gauss_off, const uint8_t* __restrict__ rate_exp, double* __restrict__ mtab)
 {
     const DProblem& P = *Pp;
-    const int n = P.n;
+    const int n = P.n, R = mtab_row(C);
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)calls * n * C;
+    long long total = (long long)calls * n * R;
     if(idx >= total) return;
-    int c = (int)(idx % C);
-    int i = (int)((idx / C) % n);
-    int call = (int)(idx / ((long long)C * n));
+    int j = (int)(idx % R);
+    int i = (int)((idx / R) % n);
+    int call = (int)(idx / ((long long)R * n));
     double m = 0.0;
-    if(c >= 2)
+    if(j < C - 2)
     {
         const int stride4 = (n + 3) / 4 * 4;
-        double r = gauss[gauss_off[call] + (size_t)(c - 2) * stride4 + i];
-        double mutation_rate = (double)(1 << rate_exp[(size_t)call * (C - 2) + (c - 2)]) * (1.0 / (double)(1 << 23)); // :265
-        double f = mutation_rate * P.genes[i].span;                                                                   // :290
-        m = r * f;                                                                                                    // :293
+        double r = gauss[gauss_off[call] + (size_t)j * stride4 + i];
+        double mutation_rate = (double)(1 << rate_exp[(size_t)call * (C - 2) + j]) * (1.0 / (double)(1 << 23)); // :265
+        double f = mutation_rate * P.genes[i].span;                                                            // :290
+        m = r * f;                                                                                             // :293
     }
     mtab[idx] = m;
 }
@@ -191,31 +201,76 @@ BIOIK_HD void joint_goal_accumulate(int type, int var_index, int i, double x, do
     }
 }
 
-#ifndef BIOIK_FAST_HELPERS_DEFINED
-#define BIOIK_FAST_HELPERS_DEFINED
-__device__ __forceinline__ uint64_t fast_fitness_key(double f) { return (f != f) ? 0xFFFFFFFFFFFFFFFFull : (uint64_t)__double_as_longlong(f); }
-__device__ __forceinline__ void fast_warp_argmin(uint64_t& key, int& pos, int& child)
+// warp argmin of (fitness key, packed position/child) with three REDUX.MIN: ties -> lowest position (:419-423)
+__device__ __forceinline__ uint32_t fast_warp_argmin(uint64_t key, uint32_t packed)
 {
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1)
-    {
-        uint64_t k2 = __shfl_xor_sync(0xffffffffu, key, o);
-        int p2 = __shfl_xor_sync(0xffffffffu, pos, o);
-        int c2 = __shfl_xor_sync(0xffffffffu, child, o);
-        if(k2 < key || (k2 == key && p2 < pos))
-        {
-            key = k2;
-            pos = p2;
-            child = c2;
-        }
-    }
+    uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    uint32_t l2 = (hi == mh) ? lo : 0xFFFFFFFFu;
+    uint32_t ml = __reduce_min_sync(0xffffffffu, l2);
+    uint32_t p2 = (hi == mh && lo == ml) ? packed : 0xFFFFFFFFu;
+    return __reduce_min_sync(0xffffffffu, p2);
 }
-#endif
+__device__ __forceinline__ uint64_t fast_fitness_key(double f) { return (f != f) ? 0xFFFFFFFFFFFFFFFEull : (uint64_t)__double_as_longlong(f); }
+constexpr uint64_t FAST_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ bool key_less(uint64_t ka, uint32_t pa, uint64_t kb, uint32_t pb) { return ka < kb || (ka == kb && pa < pb); }
 
 constexpr int FAST_MAX_CPL = 8; // population <= 256
 
-// T = tips, CH = children evaluated together per lane (register block), JOINT = joint-space goals present
-template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// fitness of one genotype under the task's approximator, by a single lane (parents at the start of a step)
+template <int T, int GSPEC, bool JOINT>
+__device__ __forceinline__ double fast_eval_one(const DProblem& P, int n, const double* x, const double* s_rec, const double* s_delta, const double* s_tip0, const double* s_gp, const double* s_jrec, const double* seed)
+{
+    double F[T][7];
+#pragma unroll
+    for(int t = 0; t < T; t++)
+#pragma unroll
+        for(int j = 0; j < 7; j++) F[t][j] = s_tip0[8 * t + j];
+    for(int i = 0; i < n; i++)
+    {
+        double d = x[i] - s_rec[4 * i + 1];
+#pragma unroll
+        for(int t = 0; t < T; t++)
+        {
+            const double* D = s_delta + ((size_t)t * n + i) * 8;
+#pragma unroll
+            for(int j = 0; j < 7; j++) F[t][j] = BIOIK_FMA(d, D[j], F[t][j]);
+        }
+    }
+    if(GSPEC == 1) return link_goal_value(G_POSE, s_gp, F[0]) * P.goals[0].weight_sq + 0.0;
+    double prim = 0.0;
+    for(int g = 0; g < P.G; g++)
+    {
+        const DGoal& gl = P.goals[g];
+        if(gl.secondary) continue;
+        double v;
+        if(JOINT && is_joint_goal(gl.type))
+        {
+            v = 0.0;
+            if(gl.type == G_JOINT_VARIABLE && gl.var_index < 0)
+            {
+                double dd = s_gp[g * GOAL_NPARAM] - seed[-1 - gl.var_index];
+                v = dd * dd;
+            }
+            else
+                for(int i = 0; i < n; i++)
+                    joint_goal_accumulate(gl.type, gl.var_index, i, x[i], s_rec[4 * i + 3], s_jrec[4 * i + 0], s_jrec[4 * i + 1], s_jrec[4 * i + 2], s_jrec[4 * i + 3], s_gp[g * GOAL_NPARAM], v);
+        }
+        else
+        {
+            double f[7];
+            select_frame<T>(F, gl.tip, f);
+            v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
+        }
+        prim += v * gl.weight_sq;
+    }
+    return prim;
+}
+
+// T = tips, CH = children evaluated together per lane (register block),
+// GSPEC = 1: the problem is exactly one primary PoseGoal (the plugin's default goal for a one-tip group);
+// JOINT: joint-space goals present (accumulated in the gene loop)
+template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds__(128, (T * CH <= 4 ? 4 : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;
@@ -226,9 +281,9 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
     const int q = task >> 1, slot = task & 1;
     if(S.done[q]) return;
     const int n = P.n, C = S.C, G = P.G;
-    const int nchunks = (C + 32 * CH - 1) / (32 * CH);
+    const int R = mtab_row(C);
+    const int nchunks = R / (32 * CH); // R is a power of two >= 32 * CH (select_evolve_fast)
 
-    // joint-space goals handled in the gene loop (host guarantees <= FAST_MAX_JOINT_GOALS)
     int nj = 0, jg_goal[FAST_MAX_JOINT_GOALS], jg_type[FAST_MAX_JOINT_GOALS], jg_var[FAST_MAX_JOINT_GOALS];
     if(JOINT)
         for(int g = 0; g < G; g++)
@@ -274,13 +329,21 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
     for(int k = lane; k < G * GOAL_NPARAM; k += 32) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
     __syncwarp();
 
-    int cur = 0; // parent buffer in use
-    const int parity = lane & 1; // child slot c = lane + 32k is even <=> lane is even
+    // Fitness of the two parents under this step's approximator.  Within a step the parents of generation
+    // g+1 are the winners of generation g, whose fitness (same genes, same operations) is already known,
+    // so children[0..1] (:381-388,:401-407) are evaluated once here and carried in registers afterwards.
+    double pf = 0.0;
+    if(lane < 2) pf = fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
+    double f_par0 = __shfl_sync(0xffffffffu, pf, 0), f_par1 = __shfl_sync(0xffffffffu, pf, 1);
+
+    int cur = 0;                 // parent buffer in use
+    const int parity = lane & 1; // child slot c = j + 2 is even <=> lane is even
+    const double wsq0 = P.goals[0].weight_sq;
 
     for(int gen = 0; gen < S.gens; gen++)
     {
         const int call = (step * 2 + slot) * S.gens + gen;
-        const double* mt = mtab + (size_t)call * n * C;
+        const double* mt = mtab + (size_t)call * n * R;
         const int child_count = P.has_secondary ? S.ccount[((size_t)q * 2 + slot) * S.gens + gen] : C;
         double* par = s_par + cur * 4 * n;
         const double *p_g0 = par, *p_g1 = par + n, *p_gr0 = par + 2 * n, *p_gr1 = par + 3 * n;
@@ -303,17 +366,21 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
         }
         __syncwarp();
 
+        // this lane's two best children so far: (key, packed = position * 512 + child)
+        uint64_t k1 = FAST_KEY_NONE, k2 = FAST_KEY_NONE;
+        uint32_t q1 = 0xFFFFFFFFu, q2 = 0xFFFFFFFFu;
+
         for(int chunk = 0; chunk < nchunks; chunk++)
         {
-            const int cbase = lane + 32 * CH * chunk;
+            const int jbase = lane + 32 * CH * chunk; // child slot c = j + 2
             double F[CH][T][7];
             double acc[JOINT ? CH : 1][FAST_MAX_JOINT_GOALS];
-            int tsel[CH];
+            const double* tp[CH]; // term column of each child: fmix class x gradient_factor (c % 3)
 #pragma unroll
             for(int k = 0; k < CH; k++)
             {
-                int c = cbase + 32 * k;
-                tsel[k] = (parity ? 3 : 0) + (c % 3); // term column: fmix class x gradient_factor (c % 3)
+                int c = jbase + 32 * k + 2;
+                tp[k] = s_term + (parity ? 3 : 0) + (c % 3);
 #pragma unroll
                 for(int t = 0; t < T; t++)
 #pragma unroll
@@ -322,45 +389,66 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
 #pragma unroll
                     for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++) acc[k][j] = 0.0;
             }
+            const double* mp = mt + jbase;
+            const double* rp = s_rec;
+            const double* dp = s_delta;
 
 #pragma unroll 1
             for(int i = 0; i < n; i++)
             {
-                const double g0 = s_rec[4 * i + 0], base = s_rec[4 * i + 1], lo = s_rec[4 * i + 2], hi = s_rec[4 * i + 3];
+                const double g0 = rp[0], base = rp[1], lo = rp[2], hi = rp[3];
                 double d[CH], x[CH];
 #pragma unroll
                 for(int k = 0; k < CH; k++)
                 {
-                    int c = cbase + 32 * k;
-                    double m = (c < C) ? BIOIK_LDG(mt + (size_t)i * C + c) : 0.0;
                     double gene = g0;
-                    gene += m;                       // gene += r * f      (:293)
-                    gene += s_term[6 * i + tsel[k]]; // gene += gradient   (:296)
-                    gene = clampd(gene, lo, hi);     // :297
-                    if(c == 0) gene = g0;            // slots 0 and 1 carry the parents unchanged (:381-388)
-                    if(c == 1) gene = p_g1[i];
+                    gene += BIOIK_LDG(mp + 32 * k); // gene += r * f      (:293)
+                    gene += tp[k][0];               // gene += gradient   (:296)
+                    gene = clampd(gene, lo, hi);    // :297
                     x[k] = gene;
                     d[k] = gene - base; // :1086
+                    tp[k] += 6;
                 }
-                const int tmask = P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
-#pragma unroll
-                for(int t = 0; t < T; t++)
+                mp += R;
+                rp += 4;
+                if(T == 1)
                 {
-                    if(!((tmask >> t) & 1)) continue; // fma(d, 0, F) == F
-                    const double* D = s_delta + ((size_t)t * n + i) * 8;
-                    const double D0 = D[0], D1 = D[1], D2 = D[2], D3 = D[3], D4 = D[4], D5 = D[5], D6 = D[6];
+                    const double D0 = dp[0], D1 = dp[1], D2 = dp[2], D3 = dp[3], D4 = dp[4], D5 = dp[5], D6 = dp[6];
 #pragma unroll
                     for(int k = 0; k < CH; k++)
                     {
-                        F[k][t][0] = BIOIK_FMA(d[k], D0, F[k][t][0]);
-                        F[k][t][1] = BIOIK_FMA(d[k], D1, F[k][t][1]);
-                        F[k][t][2] = BIOIK_FMA(d[k], D2, F[k][t][2]);
-                        F[k][t][3] = BIOIK_FMA(d[k], D3, F[k][t][3]);
-                        F[k][t][4] = BIOIK_FMA(d[k], D4, F[k][t][4]);
-                        F[k][t][5] = BIOIK_FMA(d[k], D5, F[k][t][5]);
-                        F[k][t][6] = BIOIK_FMA(d[k], D6, F[k][t][6]);
+                        F[k][0][0] = BIOIK_FMA(d[k], D0, F[k][0][0]);
+                        F[k][0][1] = BIOIK_FMA(d[k], D1, F[k][0][1]);
+                        F[k][0][2] = BIOIK_FMA(d[k], D2, F[k][0][2]);
+                        F[k][0][3] = BIOIK_FMA(d[k], D3, F[k][0][3]);
+                        F[k][0][4] = BIOIK_FMA(d[k], D4, F[k][0][4]);
+                        F[k][0][5] = BIOIK_FMA(d[k], D5, F[k][0][5]);
+                        F[k][0][6] = BIOIK_FMA(d[k], D6, F[k][0][6]);
                     }
                 }
+                else
+                {
+                    const int tmask = P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
+#pragma unroll
+                    for(int t = 0; t < T; t++)
+                    {
+                        if(!((tmask >> t) & 1)) continue; // fma(d, 0, F) == F
+                        const double* D = dp + (size_t)t * n * 8;
+                        const double D0 = D[0], D1 = D[1], D2 = D[2], D3 = D[3], D4 = D[4], D5 = D[5], D6 = D[6];
+#pragma unroll
+                        for(int k = 0; k < CH; k++)
+                        {
+                            F[k][t][0] = BIOIK_FMA(d[k], D0, F[k][t][0]);
+                            F[k][t][1] = BIOIK_FMA(d[k], D1, F[k][t][1]);
+                            F[k][t][2] = BIOIK_FMA(d[k], D2, F[k][t][2]);
+                            F[k][t][3] = BIOIK_FMA(d[k], D3, F[k][t][3]);
+                            F[k][t][4] = BIOIK_FMA(d[k], D4, F[k][t][4]);
+                            F[k][t][5] = BIOIK_FMA(d[k], D5, F[k][t][5]);
+                            F[k][t][6] = BIOIK_FMA(d[k], D6, F[k][t][6]);
+                        }
+                    }
+                }
+                dp += 8;
                 if(JOINT)
                 {
                     const double mid = s_jrec[4 * i + 0], halfspan = s_jrec[4 * i + 1], vw = s_jrec[4 * i + 2], seedv = s_jrec[4 * i + 3];
@@ -379,66 +467,84 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
 #pragma unroll
             for(int k = 0; k < CH; k++)
             {
-                const int c = cbase + 32 * k;
+                const int c = jbase + 32 * k + 2;
                 double prim = 0.0, sec = 0.0;
-                int jn = 0;
-                for(int g = 0; g < G; g++)
+                if(GSPEC == 1)
+                    prim += link_goal_value(G_POSE, s_gp, F[k][0]) * wsq0;
+                else
                 {
-                    const DGoal& gl = P.goals[g];
-                    double v;
-                    if(JOINT && is_joint_goal(gl.type))
+                    int jn = 0;
+                    for(int g = 0; g < G; g++)
                     {
-                        v = 0.0;
+                        const DGoal& gl = P.goals[g];
+                        double v;
+                        if(JOINT && is_joint_goal(gl.type))
+                        {
+                            v = 0.0;
 #pragma unroll
-                        for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
-                            if(j == jn) v = acc[k][j];
-                        if(gl.type == G_JOINT_VARIABLE && gl.var_index < 0)
-                        {
-                            double dd = s_gp[g * GOAL_NPARAM] - seed[-1 - gl.var_index];
-                            v = dd * dd;
+                            for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
+                                if(j == jn) v = acc[k][j];
+                            if(gl.type == G_JOINT_VARIABLE && gl.var_index < 0)
+                            {
+                                double dd = s_gp[g * GOAL_NPARAM] - seed[-1 - gl.var_index];
+                                v = dd * dd;
+                            }
+                            jn++;
                         }
-                        jn++;
-                    }
-                    else
-                    {
-                        double f[7];
-                        select_frame<T>(F[k], gl.secondary ? 0 : gl.tip, f);
+                        else
+                        {
+                            double f[7];
+                            select_frame<T>(F[k], gl.secondary ? 0 : gl.tip, f);
+                            if(gl.secondary)
+                            {
+                                // secondary goals see null_tip_frames (identity), src/ik_base.h:163
+                                f[0] = f[1] = f[2] = f[3] = f[4] = f[5] = 0.0;
+                                f[6] = 1.0;
+                            }
+                            v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
+                        }
                         if(gl.secondary)
-                        {
-                            // secondary goals see null_tip_frames (identity), src/ik_base.h:163
-                            f[0] = f[1] = f[2] = f[3] = f[4] = f[5] = 0.0;
-                            f[6] = 1.0;
-                        }
-                        v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
+                            sec += v * gl.weight_sq;
+                        else
+                            prim += v * gl.weight_sq;
                     }
-                    if(gl.secondary)
-                        sec += v * gl.weight_sq;
-                    else
-                        prim += v * gl.weight_sq;
                 }
-                if(c < C)
+                if(P.has_secondary)
                 {
-                    s_fit[c] = prim;
-                    s_sf[c] = sec;
+                    if(c < C)
+                    {
+                        s_fit[c] = prim;
+                        s_sf[c] = sec;
+                    }
+                }
+                else if(c < C)
+                {
+                    // running top-2 of this lane; position == child slot without pre-selection
+                    uint64_t kk = fast_fitness_key(prim);
+                    uint32_t pk = (uint32_t)c * 512u + (uint32_t)c;
+                    if(key_less(kk, pk, k1, q1))
+                    {
+                        k2 = k1; q2 = q1;
+                        k1 = kk; q1 = pk;
+                    }
+                    else if(key_less(kk, pk, k2, q2))
+                    {
+                        k2 = kk; q2 = pk;
+                    }
                 }
             }
         }
-        __syncwarp();
 
-        // ---- pre-selection positions (:366-378) and this lane's candidates ---------------------------
-        double fit[FAST_MAX_CPL];
-        int posn[FAST_MAX_CPL];
-#pragma unroll
-        for(int k = 0; k < FAST_MAX_CPL; k++)
+        if(P.has_secondary)
         {
-            int c = lane + 32 * k;
-            fit[k] = 0.0;
-            posn[k] = 0x7fffffff;
-            if(c >= C) continue;
-            fit[k] = s_fit[c];
-            posn[k] = c;
-            if(P.has_secondary && c >= 2)
+            // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
+            // child_count positions take part in the selection
+            __syncwarp();
+#pragma unroll 1
+            for(int k = 0; k < FAST_MAX_CPL; k++)
             {
+                int c = lane + 32 * k;
+                if(c < 2 || c >= C) continue;
                 double mine = s_sf[c];
                 int rank = 0;
                 for(int o = 2; o < C; o++)
@@ -446,63 +552,78 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
                     double other = s_sf[o];
                     rank += (other < mine || (other == mine && o < c)) ? 1 : 0;
                 }
-                posn[k] = (2 + rank < child_count) ? 2 + rank : 0x7fffffff;
+                if(2 + rank >= child_count) continue;
+                uint64_t kk = fast_fitness_key(s_fit[c]);
+                uint32_t pk = (uint32_t)(2 + rank) * 512u + (uint32_t)c;
+                if(key_less(kk, pk, k1, q1))
+                {
+                    k2 = k1; q2 = q1;
+                    k1 = kk; q1 = pk;
+                }
+                else if(key_less(kk, pk, k2, q2))
+                {
+                    k2 = kk; q2 = pk;
+                }
             }
         }
 
-        // ---- selection (:410-431) -------------------------------------------------------------------
-        uint64_t key = 0xFFFFFFFFFFFFFFFFull;
-        int bpos = 0x7fffffff, bchild = -1;
-#pragma unroll
-        for(int k = 0; k < FAST_MAX_CPL; k++)
+        // ---- selection (:410-431): two strict-< scans in position order ----------------------------------
+        // candidates: parent 0 at position 0, parent 1 at position 1 (cached fitness), each lane's best child
+        uint32_t w1;
         {
-            uint64_t kk = fast_fitness_key(fit[k]);
-            if(posn[k] != 0x7fffffff && (kk < key || (kk == key && posn[k] < bpos)))
+            uint64_t kk = k1;
+            uint32_t pk = q1;
+            uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
+            if(lane == 0 && key_less(kp0, 0u, kk, pk)) { kk = kp0; pk = 0u; }
+            if(lane == 1 && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
+            w1 = fast_warp_argmin(kk, pk);
+            if(f_par0 != f_par0) w1 = 0u; // position 0 holds a NaN: `f < fmin` never fires (:418-422)
+        }
+        const uint32_t w1_pos = w1 >> 9, w1_child = w1 & 511u;
+        uint32_t w2;
+        {
+            // drop winner 1; after the swap (:424) the element that was at position 0 sits at position w1_pos
+            uint64_t kk = k1;
+            uint32_t pk = q1;
+            if(pk == w1) { kk = k2; pk = q2; }
+            uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
+            if(lane == 0 && w1_child != 0u && key_less(kp0, w1_pos * 512u, kk, pk)) { kk = kp0; pk = w1_pos * 512u; }
+            if(lane == 1 && w1_child != 1u && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
+            w2 = fast_warp_argmin(kk, pk);
+            // the scan starts at position 1: its occupant wins if its fitness is NaN
+            uint32_t occ1 = (w1_pos == 1u) ? 0u : 1u;
+            double f_occ1 = occ1 == 0u ? f_par0 : f_par1;
+            if(f_occ1 != f_occ1) w2 = occ1 | (1u << 9);
+        }
+        const uint32_t w2_child = w2 & 511u;
+
+        // fitness of the winners = parents' fitness of the next generation
+        {
+            uint64_t kw1 = (k1 != FAST_KEY_NONE && q1 == w1) ? k1 : 0ull;
+            uint64_t kw2 = (k1 != FAST_KEY_NONE && q1 == w2) ? k1 : ((k2 != FAST_KEY_NONE && q2 == w2) ? k2 : 0ull);
+            // exactly one lane holds each child winner; parents keep their cached value
+            uint32_t own1 = __ballot_sync(0xffffffffu, w1_child >= 2u && q1 == w1);
+            uint32_t own2 = __ballot_sync(0xffffffffu, w2_child >= 2u && (q1 == w2 || q2 == w2));
+            double nf0 = w1_child == 0u ? f_par0 : f_par1, nf1 = w2_child == 0u ? f_par0 : f_par1;
+            if(own1)
             {
-                key = kk;
-                bpos = posn[k];
-                bchild = lane + 32 * k;
+                uint64_t kb = __shfl_sync(0xffffffffu, kw1, __ffs(own1) - 1);
+                nf0 = __longlong_as_double((long long)kb);
             }
-        }
-        fast_warp_argmin(key, bpos, bchild);
-        double f_pos0 = __shfl_sync(0xffffffffu, fit[0], 0);
-        double f_pos1 = __shfl_sync(0xffffffffu, fit[0], 1);
-        int w1_pos = bpos, w1_child = bchild;
-        if(f_pos0 != f_pos0)
-        {
-            w1_pos = 0;
-            w1_child = 0;
-        }
-        key = 0xFFFFFFFFFFFFFFFFull;
-        bpos = 0x7fffffff;
-        bchild = -1;
-#pragma unroll
-        for(int k = 0; k < FAST_MAX_CPL; k++)
-        {
-            int c = lane + 32 * k;
-            if(posn[k] == 0x7fffffff || c == w1_child) continue;
-            int p = (posn[k] == 0) ? w1_pos : posn[k];
-            uint64_t kk = fast_fitness_key(fit[k]);
-            if(kk < key || (kk == key && p < bpos))
+            if(own2)
             {
-                key = kk;
-                bpos = p;
-                bchild = c;
+                uint64_t kb = __shfl_sync(0xffffffffu, kw2, __ffs(own2) - 1);
+                nf1 = __longlong_as_double((long long)kb);
             }
-        }
-        fast_warp_argmin(key, bpos, bchild);
-        int w2_child = bchild;
-        {
-            int occ1_child = (w1_pos == 1) ? 0 : 1;
-            double f_occ1 = (occ1_child == 0) ? f_pos0 : f_pos1;
-            if(f_occ1 != f_occ1) w2_child = occ1_child;
+            f_par0 = nf0;
+            f_par1 = nf1;
         }
 
         // ---- new parents into the other buffer (lanes 0/1 re-derive the winners) -------------------
         double* nxt = s_par + (cur ^ 1) * 4 * n;
         if(lane < 2)
         {
-            const int wc = (lane == 0) ? w1_child : w2_child;
+            const int wc = (lane == 0) ? (int)w1_child : (int)w2_child;
             double* og = nxt + lane * n;        // genes of individuals[lane]
             double* ogr = nxt + (2 + lane) * n; // gradients
             if(wc < 2)
@@ -523,7 +644,7 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
                 {
                     double g0 = p_g0[i];
                     double gene = g0;
-                    gene += BIOIK_LDG(mt + (size_t)i * C + wc);
+                    gene += BIOIK_LDG(mt + (size_t)i * R + (wc - 2));
                     gene += s_term[6 * i + col];
                     gene = clampd(gene, s_rec[4 * i + 2], s_rec[4 * i + 3]);
                     og[i] = gene;
@@ -547,13 +668,16 @@ template <int T, int CH, bool JOINT> __global__ void __launch_bounds__(128) k_ev
 
 typedef void (*EvolveFastKernel)(const DProblem*, DState, int, const double*);
 
-// picks the instantiation for (tips, population, joint goals); returns nullptr if the generic kernel must be used
-inline EvolveFastKernel select_evolve_fast(int T, int C, int n_joint_goals)
+// picks the instantiation for (tips, population, goals); returns nullptr if the generic kernel must be used
+inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C)
 {
-    if(T < 1 || T > 8 || n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
-    const bool J = n_joint_goals > 0;
-    const int cpl = (C + 31) / 32;
-#define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, false>)
+    const int T = P.T;
+    if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
+    const bool J = P.n_joint_goals > 0;
+    const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);
+    const int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
+#define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
+    if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
     switch(T)
     {
     case 1: return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));

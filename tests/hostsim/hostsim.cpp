@@ -27,7 +27,7 @@ static sim_uint3 blockDim, gridDim;
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 #define __restrict__
 #define __shared__
 namespace bioik { double smem[1 << 16]; } // the `extern __shared__ double smem[]` of k_evolve
@@ -50,6 +50,30 @@ template <class T> static inline T sim_shfl(T v, int src)
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return sim_shfl(v, (int)(threadIdx.x & 31) ^ o); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return sim_shfl(v, src); }
+static inline unsigned sim_reduce_min(unsigned v)
+{
+    unsigned m = v;
+    for(int o = 16; o > 0; o >>= 1)
+    {
+        unsigned other = sim_shfl(m, (int)(threadIdx.x & 31) ^ o);
+        m = other < m ? other : m;
+    }
+    return m;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return sim_reduce_min(v); }
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    unsigned bit = pred ? (1u << (threadIdx.x & 31)) : 0u, acc = bit;
+    for(int o = 16; o > 0; o >>= 1) acc |= sim_shfl(acc, (int)(threadIdx.x & 31) ^ o);
+    return acc;
+}
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline double __longlong_as_double(long long v)
+{
+    double r;
+    memcpy(&r, &v, 8);
+    return r;
+}
 static inline long long __double_as_longlong(double d)
 {
     long long r;
@@ -173,7 +197,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    EvolveFastKernel fast = use_fast ? select_evolve_fast(P.T, S.C, P.n_joint_goals) : nullptr;
+    EvolveFastKernel fast = use_fast ? select_evolve_fast(P, S.C) : nullptr;
     if(use_fast && !fast)
     {
         g_err = "no fast kernel instantiation for this problem";
@@ -183,7 +207,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     if(fast)
     {
         int calls = (int)go.size();
-        long long total = (long long)calls * P.n * S.C;
+        long long total = (long long)calls * P.n * mtab_row(S.C);
         mtab.resize(total);
         launch_serial((int)((total + 255) / 256), 256, [&]() { k_mutation_table(&P, calls, S.C, S.gauss, S.gauss_off, S.rate_exp, mtab.data()); });
     }
