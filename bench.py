@@ -78,13 +78,26 @@ def make_workload(args, fk):
     return w, cid
 
 
+def usable_cpus():
+    """CPUs this process may actually use: min(affinity, cgroup cpu.max quota).  The GPU box exposes 128 hardware
+    threads but its container is capped (cpu.max) — oversubscribing the quota only slows the CPU arm down."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_port_rate(args, w_small, seconds, variant="fast"):
     """Times the oracle port (same source, reference flags: oracle/Makefile) on all host threads over a
     bounded sample of the workload.  Returns (solves/s, threads, sample description)."""
     import oracle_lib
     o = oracle_lib.Oracle(variant)
     cfg = oracle_lib.make_cfg(population=args.population)
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     o.tables(cfg.table_seed)
     n0 = min(len(w_small.seeds), max(64, 4 * threads))
     t0 = time.perf_counter()
@@ -109,7 +122,7 @@ def run_reference(args):
     import oracle_lib
     o = oracle_lib.Oracle("strict")
     w, cid = make_workload(args, None)
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     sample = int(min(args.batch, max(256, 256 * threads)))
     w.generate(lambda rm, pr, v: o.fk(rm, pr, v), B=sample, cfg_id=cid, seed_noise=(0.1 if args.config == "cfg4" else None))
     fast = oracle_lib.Oracle("fast")
@@ -129,7 +142,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w.name, "batch_per_step": sample, "population": args.population, "solver_steps": args.solver_steps, "generations": 8 * args.solver_steps,
                    "note": "CPU port of the reference path (reference not buildable offline); each step = bounded sample of the 10k batch"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} queries per step x {args.steps} steps"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} queries per step x {args.steps} steps", "host_hw_threads": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -290,7 +303,7 @@ def main():
         nb = B
         wcpu.goal_params, wcpu.seeds, wcpu.rng_seeds = batches[0][0][:nb], batches[0][1][:nb], batches[0][2][:nb]
         rate, threads, desc = cpu_port_rate(args, wcpu, args.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "host_hw_threads": os.cpu_count()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

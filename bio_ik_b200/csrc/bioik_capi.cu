@@ -50,6 +50,7 @@ struct bioik_ctx
     int32_t* d_gauss_off = nullptr;
     uint8_t* d_rate_exp = nullptr;
     double* d_mtab = nullptr; // [calls][n][C] mutation table of the fast generation kernel
+    SerialPlan splan;           // launch plan of the fused serial kernel (set_problem)
     bool force_generic = false; // BIOIK_FORCE_GENERIC=1: always use the generic generation kernel (tests)
 
     // state
@@ -276,6 +277,41 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
 
     k_init<<<qblocks, TPB, 0, st>>>(ctx->dP, S);
     if((rc = check_launch(ctx, "k_init")) != BIOIK_OK) return rc;
+    if(!ctx->force_generic)
+    {
+        // production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial
+        const SerialPlan& pl = ctx->splan;
+        const int sgrid = (2 * B + pl.block - 1) / pl.block;
+        if(steps > 0)
+        {
+            EventPair s0 = get_pair(ctx, 1);
+            cudaEventRecord(s0.a, st);
+            k_serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, 0, PH_PREPARE, pl.delta_smem, pl.frames_smem);
+            if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
+            cudaEventRecord(s0.b, st);
+            ctx->pending.push_back(s0);
+        }
+        for(int step = 0; step < steps; step++)
+        {
+            EventPair ev = get_pair(ctx, 0);
+            cudaEventRecord(ev.a, st);
+            if(fast)
+                fast<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step, ctx->d_mtab);
+            else
+                k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
+            if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
+            cudaEventRecord(ev.b, st);
+            ctx->pending.push_back(ev);
+            EventPair s2 = get_pair(ctx, 1);
+            cudaEventRecord(s2.a, st);
+            const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
+            k_serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, phases, pl.delta_smem, pl.frames_smem);
+            if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
+            cudaEventRecord(s2.b, st);
+            ctx->pending.push_back(s2);
+        }
+    }
+    else
     for(int step = 0; step < steps; step++)
     {
         EventPair s1 = get_pair(ctx, 1);
@@ -404,6 +440,8 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     int rc = build_problem(ctx->robot, problem, ctx->hP, ctx->error);
     if(rc != BIOIK_OK) return rc;
     CU(ctx, cudaMemcpy(ctx->dP, &ctx->hP, sizeof(DProblem), cudaMemcpyHostToDevice));
+    ctx->splan = make_serial_plan(ctx->hP);
+    if(ctx->splan.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->splan.smem_bytes));
     std::vector<double> gp((size_t)problem->n_goals * GOAL_NPARAM);
     for(int g = 0; g < problem->n_goals; g++)
         for(int k = 0; k < GOAL_NPARAM; k++) gp[(size_t)g * GOAL_NPARAM + k] = problem->goals[g].p[k];

@@ -14,6 +14,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <type_traits>
 
 #ifdef BIOIK_HOSTSIM
 #include <cmath>
@@ -109,8 +110,23 @@ struct V3 { double x, y, z; };
 struct Q4 { double x, y, z, w; };
 struct F7 { V3 p; Q4 q; };
 
-BIOIK_HD F7 load_frame(const double* f) { return F7{{f[0], f[1], f[2]}, {f[3], f[4], f[5], f[6]}}; }
-BIOIK_HD void store_frame(double* f, const F7& a)
+// Strided view: element e lives at p[e * s].  The fused serial kernel keeps per-thread arrays as
+// shared-memory COLUMNS (s = blockDim.x) so that a warp's accesses are bank-conflict free; plain
+// pointers (s = 1) work with the same templated functions.
+template <class E> struct ColT
+{
+    E* p;
+    int s;
+    BIOIK_HD E& operator[](int e) const { return p[(size_t)e * s]; }
+    BIOIK_HD ColT operator+(int e) const { return ColT{p + (size_t)e * s, s}; }
+    template <class U = E, class = typename std::enable_if<!std::is_const<U>::value>::type> BIOIK_HD operator ColT<const E>() const { return ColT<const E>{p, s}; }
+    BIOIK_HD explicit operator bool() const { return p != nullptr; }
+};
+typedef ColT<double> Col;
+typedef ColT<const double> CCol;
+
+template <class A> BIOIK_HD F7 load_frame(A f) { return F7{{f[0], f[1], f[2]}, {f[3], f[4], f[5], f[6]}}; }
+template <class A> BIOIK_HD void store_frame(A f, const F7& a)
 {
     f[0] = a.p.x; f[1] = a.p.y; f[2] = a.p.z; f[3] = a.q.x; f[4] = a.q.y; f[5] = a.q.z; f[6] = a.q.w;
 }
@@ -211,7 +227,7 @@ BIOIK_HD double clampd(double v, double lo, double hi)
 // (genesToJointVariables, src/ik_evolution_2.cpp:101-107) then updateMimic
 // (src/forward_kinematics.h:230-246)
 // ---------------------------------------------------------------------------
-BIOIK_HD void assemble_variables(const DProblem& P, const double* seed, const double* genes, double* vars)
+template <class AS, class AG, class AV> BIOIK_HD void assemble_variables(const DProblem& P, AS seed, AG genes, AV vars)
 {
     for(int v = 0; v < P.n_vars; v++)
     {
@@ -222,7 +238,7 @@ BIOIK_HD void assemble_variables(const DProblem& P, const double* seed, const do
 }
 
 // joint-local frame, src/forward_kinematics.h:78-139
-BIOIK_HD F7 joint_frame(const DSlot& S, const double* vars)
+template <class AV> BIOIK_HD F7 joint_frame(const DSlot& S, AV vars)
 {
     F7 f;
     f.p = V3{0.0, 0.0, 0.0};
@@ -244,7 +260,7 @@ BIOIK_HD F7 joint_frame(const DSlot& S, const double* vars)
 
 // RobotFK_Fast_Base::applyConfiguration, src/forward_kinematics.h:331-354.
 // frames: [L][7] scratch (global frames of the scheduled links).
-BIOIK_HD void exact_fk(const DProblem& P, const double* vars, double* frames)
+template <class AV, class AF> BIOIK_HD void exact_fk(const DProblem& P, AV vars, AF frames)
 {
     for(int s = 0; s < P.L; s++)
     {
@@ -263,7 +279,7 @@ BIOIK_HD void exact_fk(const DProblem& P, const double* vars, double* frames)
 // RobotFK_Jacobian::computeJacobian (src/forward_kinematics.h:600-730) fused with
 // RobotFK_Mutator::initializeMutationApproximator (:802-930) for one (gene, tip):
 // returns the delta frame; *masked = the :919-926 test.
-BIOIK_HD F7 delta_frame(const DProblem& P, const double* frames, int gene, int tip, bool& masked)
+template <class AF> BIOIK_HD F7 delta_frame(const DProblem& P, AF frames, int gene, int tip, bool& masked)
 {
     const DGene& Gn = P.genes[gene];
     F7 tipf = load_frame(frames + 7 * P.tip_slot[tip]);
@@ -307,12 +323,12 @@ BIOIK_HD F7 delta_frame(const DProblem& P, const double* frames, int gene, int t
 
 // computeApproximateMutations for one genotype, src/forward_kinematics.h:1061-1110 (AVX+FMA form).
 // tip0 [T][7], delta [T][n][7] (zero where unmasked), base [n], x [n] -> out [T][7]
-BIOIK_HD void approx_frames(int T, int n, const double* tip0, const double* delta, const double* base, const double* x, double* out)
+template <class A0, class AD, class AB, class AX, class AO> BIOIK_HD void approx_frames(int T, int n, A0 tip0, AD delta, AB base, AX x, AO out)
 {
     for(int t = 0; t < T; t++)
     {
         double f0 = tip0[7 * t + 0], f1 = tip0[7 * t + 1], f2 = tip0[7 * t + 2], f3 = tip0[7 * t + 3], f4 = tip0[7 * t + 4], f5 = tip0[7 * t + 5], f6 = tip0[7 * t + 6];
-        const double* D = delta + (size_t)t * n * 7;
+        AD D = delta + t * n * 7;
         for(int i = 0; i < n; i++)
         {
             double d = x[i] - base[i]; // :1086
@@ -330,11 +346,11 @@ BIOIK_HD void approx_frames(int T, int n, const double* tip0, const double* delt
 
 // computeApproximateMutation1, src/forward_kinematics.h:933-964 (AVX+FMA form), with the
 // intended semantics for tips the variable does not influence (zero delta => copy)
-BIOIK_HD void approx_frames1(int T, int n, const double* delta, int gene, double dv, const double* in, double* out)
+template <class AD, class AI, class AO> BIOIK_HD void approx_frames1(int T, int n, AD delta, int gene, double dv, AI in, AO out)
 {
     for(int t = 0; t < T; t++)
     {
-        const double* D = delta + ((size_t)t * n + gene) * 7;
+        AD D = delta + (t * n + gene) * 7;
         for(int k = 0; k < 7; k++) out[7 * t + k] = BIOIK_FMA(dv, D[k], in[7 * t + k]);
     }
 }
@@ -348,9 +364,9 @@ BIOIK_HD void approx_frames1(int T, int n, const double* delta, int gene, double
 BIOIK_HD double len2(double x, double y, double z) { return x * x + y * y + z * z; }
 BIOIK_HD double qlen2(double x, double y, double z, double w) { return x * x + y * y + z * z + w * w; }
 
-BIOIK_HD double goal_value(const DProblem& P, const DGoal& g, const double* p, const double* tips, const double* x, const double* seed)
+template <class AP, class AT, class AX, class AS> BIOIK_HD double goal_value(const DProblem& P, const DGoal& g, AP p, AT tips, AX x, AS seed)
 {
-    const double* f = tips + 7 * g.tip;
+    AT f = tips + 7 * g.tip;
     switch(g.type)
     {
     case G_POSITION: // goal_types.h:96: tf2 distance2(v) = (v - this).length2()
@@ -472,6 +488,23 @@ static const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 
 #else
 static __device__ const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
 #endif
+
+template <class AP, class AT, class AX, class AS> BIOIK_HD double goal_fitness_t(const DProblem& P, int which, AP gp, AT tips, AX x, AS seed)
+{
+    double sum = 0.0;
+    for(int g = 0; g < P.G; g++)
+    {
+        if(P.goals[g].secondary != which) continue;
+        sum += goal_value(P, P.goals[g], gp + g * GOAL_NPARAM, tips, x, seed) * P.goals[g].weight_sq;
+    }
+    return sum;
+}
+// secondary goals (which = 1) evaluated on the null tip frames
+template <class AP, class AX, class AS> BIOIK_HD double goal_fitness_secondary(const DProblem& P, AP gp, AX x, AS seed)
+{
+    const double* nt = NULL_TIPS;
+    return goal_fitness_t(P, 1, gp, nt, x, seed);
+}
 
 BIOIK_HD double goal_fitness(const DProblem& P, int which, const double* gp, const double* tips, const double* x, const double* seed)
 {
@@ -597,13 +630,13 @@ BIOIK_HD double angle_shortest_path(const Q4& a, const Q4& b)
     if(d < 0) return BIOIK_ACOS((a.x * -b.x + a.y * -b.y + a.z * -b.z + a.w * -b.w) / s) * 2.0;
     return BIOIK_ACOS(d / s) * 2.0;
 }
-BIOIK_HD bool check_solution(const DProblem& P, const double* gp, const double* tips, const double* x, const double* seed)
+template <class AP, class AT, class AX, class AS> BIOIK_HD bool check_solution(const DProblem& P, AP gp, AT tips, AX x, AS seed)
 {
     for(int gi = 0; gi < P.G; gi++)
     {
         const DGoal& g = P.goals[gi];
         if(g.secondary) continue;
-        const double* p = gp + gi * GOAL_NPARAM;
+        AP p = gp + gi * GOAL_NPARAM;
         F7 fb = load_frame(tips + 7 * g.tip);
         F7 fa;
         fa.p = V3{0, 0, 0};

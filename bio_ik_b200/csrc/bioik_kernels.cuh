@@ -605,3 +605,4 @@ __global__ void k_approx_fitness(const DProblem* __restrict__ Pp, int B, int M, 
 } // namespace bioik
 
 #include "bioik_evolve_fast.cuh"
+#include "bioik_serial.cuh"

@@ -30,7 +30,7 @@ static sim_uint3 blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __restrict__
 #define __shared__
-namespace bioik { double smem[1 << 16]; } // the `extern __shared__ double smem[]` of k_evolve
+namespace bioik { double smem[1 << 18]; } // the `extern __shared__ double smem[]` of k_evolve
 
 static std::barrier<>* g_warp_barrier = nullptr;
 static uint64_t g_shfl_slots[32];
@@ -212,16 +212,28 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         launch_serial((int)((total + 255) / 256), 256, [&]() { k_mutation_table(&P, calls, S.C, S.gauss, S.gauss_off, S.rate_exp, mtab.data()); });
     }
     launch_serial(qblocks, TPB, [&]() { k_init(&P, S); });
-    for(int step = 0; step < steps; step++)
+    if(use_fast)
     {
-        launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S); });
-        if(fast)
+        // production launch sequence of enqueue_solve(): k_evolve_fast + the fused k_serial (32-thread blocks here)
+        SerialPlan pl = make_serial_plan(P);
+        const int sgrid = (2 * B + 31) / 32;
+        if(steps > 0) launch_warp(sgrid, [&]() { k_serial(P, S, 0, PH_PREPARE, pl.delta_smem, pl.frames_smem); });
+        for(int step = 0; step < steps; step++)
+        {
             launch_warp(2 * B, [&]() { fast(&P, S, step, mtab.data()); });
-        else
-            launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
-        if(S.memetic) launch_serial(tblocks, TPB, [&]() { k_memetic(&P, S, step); });
-        launch_serial(qblocks, TPB, [&]() { k_species(&P, S, step); });
+            const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
+            launch_warp(sgrid, [&]() { k_serial(P, S, step, phases, pl.delta_smem, pl.frames_smem); });
+        }
     }
+    else
+        for(int step = 0; step < steps; step++)
+        {
+            // the generic kernels (BIOIK_FORCE_GENERIC=1 path of the library)
+            launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S); });
+            launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
+            if(S.memetic) launch_serial(tblocks, TPB, [&]() { k_memetic(&P, S, step); });
+            launch_serial(qblocks, TPB, [&]() { k_species(&P, S, step); });
+        }
     launch_serial(qblocks, TPB, [&]() { k_finalize(&P, S, out_solutions, out_fitness, out_success, out_steps); });
     if(out_genes) memcpy(out_genes, genes.data(), genes.size() * 8);
     if(out_gradients) memcpy(out_gradients, grads.data(), grads.size() * 8);
