@@ -51,6 +51,7 @@ struct bioik_ctx
     uint8_t* d_rate_exp = nullptr;
     double* d_mtab = nullptr; // [calls][n][C] mutation table of the fast generation kernel
     SerialPlan splan;           // launch plan of the fused serial kernel (set_problem)
+    SerialKernel serial = nullptr;
     bool force_generic = false; // BIOIK_FORCE_GENERIC=1: always use the generic generation kernel (tests)
 
     // state
@@ -286,7 +287,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         {
             EventPair s0 = get_pair(ctx, 1);
             cudaEventRecord(s0.a, st);
-            k_serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, 0, PH_PREPARE, pl.delta_smem, pl.frames_smem);
+            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, 0, PH_PREPARE);
             if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
             cudaEventRecord(s0.b, st);
             ctx->pending.push_back(s0);
@@ -305,7 +306,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
             EventPair s2 = get_pair(ctx, 1);
             cudaEventRecord(s2.a, st);
             const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
-            k_serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, phases, pl.delta_smem, pl.frames_smem);
+            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, phases);
             if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
             cudaEventRecord(s2.b, st);
             ctx->pending.push_back(s2);
@@ -441,7 +442,8 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     if(rc != BIOIK_OK) return rc;
     CU(ctx, cudaMemcpy(ctx->dP, &ctx->hP, sizeof(DProblem), cudaMemcpyHostToDevice));
     ctx->splan = make_serial_plan(ctx->hP);
-    if(ctx->splan.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->splan.smem_bytes));
+    ctx->serial = select_serial(ctx->splan);
+    if(ctx->splan.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->splan.smem_bytes));
     std::vector<double> gp((size_t)problem->n_goals * GOAL_NPARAM);
     for(int g = 0; g < problem->n_goals; g++)
         for(int k = 0; k < GOAL_NPARAM; k++) gp[(size_t)g * GOAL_NPARAM + k] = problem->goals[g].p[k];

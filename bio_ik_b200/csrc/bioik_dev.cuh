@@ -125,6 +125,16 @@ template <class E> struct ColT
 typedef ColT<double> Col;
 typedef ColT<const double> CCol;
 
+// same with a compile-time stride (lets the compiler fold the stride into immediates and keep the
+// shared-memory address space of the base pointer)
+template <class E, int S> struct FixedCol
+{
+    E* p;
+    BIOIK_HD E& operator[](int e) const { return p[e * S]; }
+    BIOIK_HD FixedCol operator+(int e) const { return FixedCol{p + e * S}; }
+    template <class U = E, class = typename std::enable_if<!std::is_const<U>::value>::type> BIOIK_HD operator FixedCol<const E, S>() const { return FixedCol<const E, S>{p}; }
+};
+
 template <class A> BIOIK_HD F7 load_frame(A f) { return F7{{f[0], f[1], f[2]}, {f[3], f[4], f[5], f[6]}}; }
 template <class A> BIOIK_HD void store_frame(A f, const F7& a)
 {

@@ -55,17 +55,24 @@ inline SerialPlan make_serial_plan(const DProblem& P, size_t smem_limit = 200 * 
     return pl; // 32 threads, delta + frames off chip: always fits (fixed part <= ~1 KB/thread)
 }
 
-template <class AT> BIOIK_HD void copy_tips(const DProblem& P, CCol frames, AT tips)
+template <class AF, class AT> BIOIK_HD void copy_tips(const DProblem& P, AF frames, AT tips)
 {
     for(int t = 0; t < P.T; t++)
         for(int k = 0; k < 7; k++) tips[7 * t + k] = frames[7 * P.tip_slot[t] + k];
 }
 
-__global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, int step, int phases, int delta_smem, int frames_smem)
+// BS = threads per block (column stride), DS = delta frames in shared memory, FS = link frames in shared memory
+template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_serial(BIOIK_PROBLEM_PARAM, DState S, int step, int phases)
 {
     extern __shared__ double smem[];
-    const int tid = threadIdx.x, bs = blockDim.x;
-    const int task_raw = blockIdx.x * bs + tid;
+    typedef FixedCol<double, BS> SC;         // shared-memory column
+    typedef FixedCol<const double, BS> CSC;
+    typedef FixedCol<double, 1> GC;          // plain array (global / local)
+    typedef typename std::conditional<DS, SC, GC>::type DeltaCol;
+    typedef typename std::conditional<FS, SC, GC>::type FrameCol;
+
+    const int tid = threadIdx.x;
+    const int task_raw = blockIdx.x * BS + tid;
     const bool valid = task_raw < 2 * S.B;
     const int task = valid ? task_raw : 2 * S.B - 1;
     const int q = task >> 1, slot = task & 1;
@@ -75,21 +82,22 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
     // ---- per-thread columns --------------------------------------------------------------------
     int off = 0;
     auto col = [&](int len) {
-        Col c{smem + (size_t)off * bs + tid, bs};
+        SC c{smem + off * BS + tid};
         off += len;
         return c;
     };
-    Col ind = col(n), temp = col(n), grad = col(n), stash = col(n), ph2 = col(7 * T), ph3 = col(7 * T), tip0 = col(7 * T), base = col(n), gp = col(GOAL_NPARAM * G), vars = col(P.n_vars);
-    Col delta, frames;
-    if(delta_smem)
-        delta = col(7 * T * n);
+    const SC ind = col(n), temp = col(n), grad = col(n), stash = col(n), ph2 = col(7 * T), ph3 = col(7 * T), tip0 = col(7 * T), base = col(n), gp = col(GOAL_NPARAM * G), vars = col(P.n_vars);
+    DeltaCol delta;
+    if(DS)
+        delta.p = smem + off * BS + tid, off += 7 * T * n;
     else
-        delta = Col{S.delta + (size_t)task * T * n * 7, 1};
-    double lf[MAX_SLOTS * 7]; // only touched when the link frames do not fit in shared memory
-    if(frames_smem)
-        frames = col(7 * P.L);
+        delta.p = S.delta + (size_t)task * T * n * 7;
+    double lf[FS ? 1 : MAX_SLOTS * 7]; // link frames in thread-local memory only when they do not fit on chip
+    FrameCol frames;
+    if(FS)
+        frames.p = smem + off * BS + tid, off += 7 * P.L;
     else
-        frames = Col{lf, 1};
+        frames.p = lf;
 
     const double* seed = S.seeds + (size_t)q * P.n_vars;
     if(active)
@@ -99,9 +107,15 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
         const double* gi = S.genes + ((size_t)task * 2 + 0) * n;
         for(int i = 0; i < n; i++) ind[i] = gi[i];
     }
-    CCol cgp = gp;
+    const CSC cgp = gp;
 
     // ---- MEMETIC (src/ik_evolution_2.cpp:436-570) ----------------------------------------------------
+    // One evaluation site: the n+4 evaluations of an iteration run through the same loop body
+    //   e = 0        x = genes                    full approximation -> ph2   f2p, fa        (:460-464)
+    //   e = 1..n     x = genes + dp e_(e-1)       one-variable update of ph2 -> ph3   gradient[e-1] (:465-474)
+    //   e = n+1      x = genes - gradient         full -> ph3                 f1             (:485-488)
+    //   e = n+2      x = genes + gradient         full -> ph3                 f3             (:492-495)
+    //   e = n+3      x = clip(genes +- gradient * step)  full -> ph2          f4p (primary)  (:525-527 / :554-556)
     if(active && (phases & PH_MEMETIC) && S.memetic)
     {
         {
@@ -109,65 +123,82 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
             for(int k = 0; k < 7 * T; k++) tip0[k] = t0[k];
             const double* b0 = S.base + (size_t)task * n;
             for(int i = 0; i < n; i++) base[i] = b0[i];
-            if(delta_smem)
+            if(DS)
             {
                 const double* d0 = S.delta + (size_t)task * T * n * 7;
                 for(int k = 0; k < 7 * T * n; k++) delta[k] = d0[k];
             }
         }
-        CCol cdelta = delta, ctip0 = tip0, cbase = base;
-        double dp = 0.0000001;                               // :450
+        double dp = 0.0000001;                                                                                // :450
         if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
+        const bool quad = S.memetic == 'q';
         for(int generation = 0; generation < S.memetic_iters; generation++)
         {
-            for(int i = 0; i < n; i++) temp[i] = ind[i];       // :460
-            approx_frames(T, n, ctip0, cdelta, cbase, CCol(temp), ph2); // :462
-            double f2p = goal_fitness_t(P, 0, cgp, CCol(ph2), CCol(temp), seed);                       // :463
-            double fa = f2p + (P.has_secondary ? goal_fitness_secondary(P, cgp, CCol(temp), seed) : 0.0); // :464
-            for(int i = 0; i < n; i++)                           // :465-474
+            double f2p = 0.0, fa = 0.0, f1 = 0.0, f3 = 0.0, f4p = 0.0;
+            for(int i = 0; i < n; i++) temp[i] = ind[i]; // :460
+            for(int e = 0; e < n + 4; e++)
             {
-                temp[i] = ind[i] + dp;
-                approx_frames1(T, n, cdelta, i, dp, CCol(ph2), ph3);
-                double fb = 0.0;
-                fb += goal_fitness_t(P, 0, cgp, CCol(ph3), CCol(temp), seed);
-                fb += P.has_secondary ? goal_fitness_secondary(P, cgp, CCol(temp), seed) : 0.0;
-                temp[i] = ind[i];
-                grad[i] = fb - fa;
+                const bool single = (e >= 1 && e <= n);
+                if(single)
+                    temp[e - 1] = ind[e - 1] + dp; // :468
+                else if(e == n + 1)
+                {
+                    // normalise the gradient (:477-482), then the first support point (:485-486)
+                    double sum = dp * dp;
+                    for(int i = 0; i < n; i++) sum += BIOIK_FABS(grad[i]);
+                    double f = 1.0 / sum * dp;
+                    for(int i = 0; i < n; i++) grad[i] *= f;
+                    for(int i = 0; i < n; i++) temp[i] = ind[i] - grad[i];
+                }
+                else if(e == n + 2)
+                    for(int i = 0; i < n; i++) temp[i] = ind[i] + grad[i]; // :492-493
+                else if(e == n + 3)
+                {
+                    const double f2 = fa;
+                    if(quad) // :502-506,:525
+                    {
+                        double v1 = (f2 - f1);
+                        double v2 = (f3 - f2);
+                        double v = (v1 + v2) * 0.5;
+                        double a = (v1 - v2);
+                        double step_size = v / a;
+                        for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] + grad[i] * step_size * 1.0, P.genes[i].clip_min, P.genes[i].clip_max);
+                    }
+                    else // :549-554
+                    {
+                        double cost_diff = (f3 - f1) * 0.5;
+                        double step_size = f2 / cost_diff;
+                        for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] - grad[i] * step_size, P.genes[i].clip_min, P.genes[i].clip_max);
+                    }
+                }
+                // genotype -> phenotype
+                const bool to_ph2 = (e == 0 || e == n + 3);
+                const SC out = to_ph2 ? ph2 : ph3;
+                if(single)
+                    approx_frames1(T, n, delta, e - 1, dp, CSC(ph2), ph3); // :469
+                else
+                    approx_frames(T, n, CSC(tip0), delta, CSC(base), CSC(temp), out); // :462,:487,:494,:526
+                // fitness: primary + secondary (computeCombinedFitnessActiveVariables, src/ik_base.h:179-185)
+                const double prim = goal_fitness_t(P, 0, cgp, CSC(out), CSC(temp), seed);
+                double comb = prim;
+                if(e != n + 3) comb = prim + (P.has_secondary ? goal_fitness_secondary(P, cgp, CSC(temp), seed) : 0.0);
+                if(e == 0)
+                {
+                    f2p = prim;
+                    fa = comb;
+                }
+                else if(single)
+                {
+                    temp[e - 1] = ind[e - 1]; // :471
+                    grad[e - 1] = comb - fa;  // :472-473
+                }
+                else if(e == n + 1)
+                    f1 = comb;
+                else if(e == n + 2)
+                    f3 = comb;
+                else
+                    f4p = prim;
             }
-            double sum = dp * dp; // :477-482
-            for(int i = 0; i < n; i++) sum += BIOIK_FABS(grad[i]);
-            double f = 1.0 / sum * dp;
-            for(int i = 0; i < n; i++) grad[i] *= f;
-
-            for(int i = 0; i < n; i++) temp[i] = ind[i] - grad[i]; // :485-488
-            approx_frames(T, n, ctip0, cdelta, cbase, CCol(temp), ph3);
-            double f1 = 0.0;
-            f1 += goal_fitness_t(P, 0, cgp, CCol(ph3), CCol(temp), seed);
-            f1 += P.has_secondary ? goal_fitness_secondary(P, cgp, CCol(temp), seed) : 0.0;
-            double f2 = fa;
-            for(int i = 0; i < n; i++) temp[i] = ind[i] + grad[i]; // :492-495
-            approx_frames(T, n, ctip0, cdelta, cbase, CCol(temp), ph3);
-            double f3 = 0.0;
-            f3 += goal_fitness_t(P, 0, cgp, CCol(ph3), CCol(temp), seed);
-            f3 += P.has_secondary ? goal_fitness_secondary(P, cgp, CCol(temp), seed) : 0.0;
-
-            if(S.memetic == 'q') // :498-542
-            {
-                double v1 = (f2 - f1);
-                double v2 = (f3 - f2);
-                double v = (v1 + v2) * 0.5;
-                double a = (v1 - v2);
-                double step_size = v / a;
-                for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] + grad[i] * step_size * 1.0, P.genes[i].clip_min, P.genes[i].clip_max); // :525
-            }
-            else // 'l', :545-568
-            {
-                double cost_diff = (f3 - f1) * 0.5;
-                double step_size = f2 / cost_diff;
-                for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] - grad[i] * step_size, P.genes[i].clip_min, P.genes[i].clip_max); // :554
-            }
-            approx_frames(T, n, ctip0, cdelta, cbase, CCol(temp), ph2);
-            double f4p = goal_fitness_t(P, 0, cgp, CCol(ph2), CCol(temp), seed);
             if(f4p < f2p) // :530-538 / :559-567
             {
                 for(int i = 0; i < n; i++) ind[i] = temp[i];
@@ -186,10 +217,10 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
         double f = 0.0;
         if(active)
         {
-            assemble_variables(P, seed, CCol(ind), vars); // genesToJointVariables :610
-            exact_fk(P, CCol(vars), frames);               // computeFitness :611 -> applyConfiguration
-            copy_tips(P, CCol(frames), ph2);
-            f = goal_fitness_t(P, 0, cgp, CCol(ph2), CCol(ind), seed);
+            assemble_variables(P, seed, CSC(ind), vars); // genesToJointVariables :610
+            exact_fk(P, CSC(vars), frames);               // computeFitness :611 -> applyConfiguration
+            copy_tips(P, frames, ph2);
+            f = goal_fitness_t(P, 0, cgp, CSC(ph2), CSC(ind), seed);
             frames_valid = true;
         }
         const double fo = __shfl_xor_sync(0xffffffffu, f, 1);
@@ -253,19 +284,22 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
                 S.steps[q] = steps;
                 if((steps % 4) == 0 || steps == S.total_steps)
                 {
-                    int ok;
-                    if(sol_is_ind)
-                        ok = check_solution(P, cgp, CCol(ph2), CCol(ind), seed) ? 1 : 0;
-                    else
+                    // getSolution() -> exact FK -> checkSolution.  If the solution is this species' individual
+                    // its exact tip frames are already in ph2; otherwise recompute them (frames/vars are scratch).
+                    // grads of individual 1 are parked in `stash`, individual 1 genes in `temp`: use base/ph3.
+                    SC xs = ind, ts = ph2;
+                    if(!sol_is_ind)
                     {
-                        // exact FK of the (older) solution; frames/vars/ph3 are scratch here
                         const double* sol = S.sol + (size_t)q * n;
-                        assemble_variables(P, seed, sol, vars);
-                        exact_fk(P, CCol(vars), frames);
-                        copy_tips(P, CCol(frames), ph3);
-                        ok = check_solution(P, cgp, CCol(ph3), sol, seed) ? 1 : 0;
+                        for(int i = 0; i < n; i++) base[i] = sol[i];
+                        assemble_variables(P, seed, CSC(base), vars);
+                        exact_fk(P, CSC(vars), frames);
+                        copy_tips(P, frames, ph3);
                         frames_valid = false;
+                        xs = base;
+                        ts = ph3;
                     }
+                    const int ok = check_solution(P, cgp, CSC(ts), CSC(xs), seed) ? 1 : 0;
                     S.success[q] = ok;
                     if(ok && S.early_exit) S.done[q] = 1;
                 }
@@ -293,27 +327,40 @@ __global__ void __launch_bounds__(128) k_serial(BIOIK_PROBLEM_PARAM, DState S, i
     // ---- PREPARE (src/ik_evolution_2.cpp:341-346) ---------------------------------------------------------
     if(active && (phases & PH_PREPARE))
     {
-        if(!frames_valid)
-        {
-            assemble_variables(P, seed, CCol(ind), vars);
-            exact_fk(P, CCol(vars), frames);
-        }
+        // p_variables = post-mimic variables of the base configuration (:1063)
+        assemble_variables(P, seed, CSC(ind), vars);
+        if(!frames_valid) exact_fk(P, CSC(vars), frames);
         double* t0 = S.tip0 + (size_t)my_task * T * 7;
         for(int t = 0; t < T; t++)
             for(int k = 0; k < 7; k++) t0[7 * t + k] = frames[7 * P.tip_slot[t] + k];
         double* b0 = S.base + (size_t)my_task * n;
-        // p_variables = post-mimic variables of the base configuration (:1063): for an active,
-        // non-mimic variable that is the gene itself
-        assemble_variables(P, seed, CCol(ind), vars);
         for(int i = 0; i < n; i++) b0[i] = vars[P.genes[i].var];
         double* d0 = S.delta + (size_t)my_task * T * n * 7;
         for(int t = 0; t < T; t++)
             for(int i = 0; i < n; i++)
             {
                 bool masked;
-                store_frame(d0 + ((size_t)t * n + i) * 7, delta_frame(P, CCol(frames), i, t, masked));
+                store_frame(d0 + ((size_t)t * n + i) * 7, delta_frame(P, frames, i, t, masked));
             }
     }
+}
+
+#ifdef BIOIK_HOSTSIM
+typedef void (*SerialKernel)(const DProblem&, DState, int, int);
+#else
+typedef void (*SerialKernel)(const DProblem, DState, int, int);
+#endif
+
+inline SerialKernel select_serial(const SerialPlan& pl)
+{
+#define BIOIK_SER(BS) (pl.delta_smem ? (SerialKernel)k_serial<BS, true, true> : (pl.frames_smem ? (SerialKernel)k_serial<BS, false, true> : (SerialKernel)k_serial<BS, false, false>))
+    switch(pl.block)
+    {
+    case 128: return BIOIK_SER(128);
+    case 64: return BIOIK_SER(64);
+    default: return BIOIK_SER(32);
+    }
+#undef BIOIK_SER
 }
 
 } // namespace bioik

@@ -216,13 +216,15 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     {
         // production launch sequence of enqueue_solve(): k_evolve_fast + the fused k_serial (32-thread blocks here)
         SerialPlan pl = make_serial_plan(P);
+        pl.block = 32;
+        SerialKernel ks = select_serial(pl);
         const int sgrid = (2 * B + 31) / 32;
-        if(steps > 0) launch_warp(sgrid, [&]() { k_serial(P, S, 0, PH_PREPARE, pl.delta_smem, pl.frames_smem); });
+        if(steps > 0) launch_warp(sgrid, [&]() { ks(P, S, 0, PH_PREPARE); });
         for(int step = 0; step < steps; step++)
         {
             launch_warp(2 * B, [&]() { fast(&P, S, step, mtab.data()); });
             const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
-            launch_warp(sgrid, [&]() { k_serial(P, S, step, phases, pl.delta_smem, pl.frames_smem); });
+            launch_warp(sgrid, [&]() { ks(P, S, step, phases); });
         }
     }
     else
