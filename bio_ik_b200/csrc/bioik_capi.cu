@@ -52,6 +52,7 @@ struct bioik_ctx
     double* d_mtab = nullptr; // [calls][n][C] mutation table of the fast generation kernel
     SerialPlan splan;           // launch plan of the fused serial kernel (set_problem)
     SerialKernel serial = nullptr;
+    int sm_count = 148;
     bool force_generic = false; // BIOIK_FORCE_GENERIC=1: always use the generic generation kernel (tests)
 
     // state
@@ -281,7 +282,10 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     if(!ctx->force_generic)
     {
         // production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial
+        ctx->splan = make_serial_plan(P, 2 * B, ctx->sm_count);
+        ctx->serial = select_serial(ctx->splan);
         const SerialPlan& pl = ctx->splan;
+        if(pl.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
         const int sgrid = (2 * B + pl.block - 1) / pl.block;
         if(steps > 0)
         {
@@ -411,6 +415,7 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         return fail(nullptr, BIOIK_E_CUDA, msg);
     }
     memset(&ctx->S, 0, sizeof(ctx->S));
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
     {
         const char* fg = getenv("BIOIK_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
@@ -441,9 +446,7 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     int rc = build_problem(ctx->robot, problem, ctx->hP, ctx->error);
     if(rc != BIOIK_OK) return rc;
     CU(ctx, cudaMemcpy(ctx->dP, &ctx->hP, sizeof(DProblem), cudaMemcpyHostToDevice));
-    ctx->splan = make_serial_plan(ctx->hP);
-    ctx->serial = select_serial(ctx->splan);
-    if(ctx->splan.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->splan.smem_bytes));
+
     std::vector<double> gp((size_t)problem->n_goals * GOAL_NPARAM);
     for(int g = 0; g < problem->n_goals; g++)
         for(int k = 0; k < GOAL_NPARAM; k++) gp[(size_t)g * GOAL_NPARAM + k] = problem->goals[g].p[k];

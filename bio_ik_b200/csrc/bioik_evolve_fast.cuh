@@ -18,6 +18,8 @@
 
 #include "bioik_dev.cuh"
 
+#include <type_traits>
+
 #ifdef BIOIK_HOSTSIM
 #define BIOIK_LDG(p) (*(p))
 #else
@@ -381,10 +383,6 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
             {
                 int c = jbase + 32 * k + 2;
                 tp[k] = s_term + (parity ? 3 : 0) + (c % 3);
-#pragma unroll
-                for(int t = 0; t < T; t++)
-#pragma unroll
-                    for(int j = 0; j < 7; j++) F[k][t][j] = s_tip0[8 * t + j];
                 if(JOINT)
 #pragma unroll
                     for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++) acc[k][j] = 0.0;
@@ -393,60 +391,50 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
             const double* rp = s_rec;
             const double* dp = s_delta;
 
-#pragma unroll 1
-            for(int i = 0; i < n; i++)
-            {
+            // mutation terms are fetched one gene ahead of their use (L1/L2 latency off the dependent chain)
+            double mnext[CH];
+#pragma unroll
+            for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
+
+            // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
+            auto gene_step = [&](auto first_tag, int i) {
+                constexpr bool FIRST = decltype(first_tag)::value;
                 const double g0 = rp[0], base = rp[1], lo = rp[2], hi = rp[3];
-                double d[CH], x[CH];
+                double d[CH], x[CH], m[CH];
+#pragma unroll
+                for(int k = 0; k < CH; k++) m[k] = mnext[k];
+                mp += R;
+                if(i + 1 < n)
+                {
+#pragma unroll
+                    for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
+                }
 #pragma unroll
                 for(int k = 0; k < CH; k++)
                 {
                     double gene = g0;
-                    gene += BIOIK_LDG(mp + 32 * k); // gene += r * f      (:293)
-                    gene += tp[k][0];               // gene += gradient   (:296)
-                    gene = clampd(gene, lo, hi);    // :297
+                    gene += m[k];                // gene += r * f      (:293)
+                    gene += tp[k][0];            // gene += gradient   (:296)
+                    gene = clampd(gene, lo, hi); // :297
                     x[k] = gene;
                     d[k] = gene - base; // :1086
                     tp[k] += 6;
                 }
-                mp += R;
                 rp += 4;
-                if(T == 1)
+                const int tmask = (T == 1) ? 1 : P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
+#pragma unroll
+                for(int t = 0; t < T; t++)
                 {
-                    const double D0 = dp[0], D1 = dp[1], D2 = dp[2], D3 = dp[3], D4 = dp[4], D5 = dp[5], D6 = dp[6];
+                    const bool on = (tmask >> t) & 1;
+                    if(!on && !FIRST) continue; // fma(d, 0, F) == F
+                    const double* D = dp + (size_t)t * n * 8;
+                    double Dv[7];
+#pragma unroll
+                    for(int j = 0; j < 7; j++) Dv[j] = on ? D[j] : 0.0;
 #pragma unroll
                     for(int k = 0; k < CH; k++)
-                    {
-                        F[k][0][0] = BIOIK_FMA(d[k], D0, F[k][0][0]);
-                        F[k][0][1] = BIOIK_FMA(d[k], D1, F[k][0][1]);
-                        F[k][0][2] = BIOIK_FMA(d[k], D2, F[k][0][2]);
-                        F[k][0][3] = BIOIK_FMA(d[k], D3, F[k][0][3]);
-                        F[k][0][4] = BIOIK_FMA(d[k], D4, F[k][0][4]);
-                        F[k][0][5] = BIOIK_FMA(d[k], D5, F[k][0][5]);
-                        F[k][0][6] = BIOIK_FMA(d[k], D6, F[k][0][6]);
-                    }
-                }
-                else
-                {
-                    const int tmask = P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
 #pragma unroll
-                    for(int t = 0; t < T; t++)
-                    {
-                        if(!((tmask >> t) & 1)) continue; // fma(d, 0, F) == F
-                        const double* D = dp + (size_t)t * n * 8;
-                        const double D0 = D[0], D1 = D[1], D2 = D[2], D3 = D[3], D4 = D[4], D5 = D[5], D6 = D[6];
-#pragma unroll
-                        for(int k = 0; k < CH; k++)
-                        {
-                            F[k][t][0] = BIOIK_FMA(d[k], D0, F[k][t][0]);
-                            F[k][t][1] = BIOIK_FMA(d[k], D1, F[k][t][1]);
-                            F[k][t][2] = BIOIK_FMA(d[k], D2, F[k][t][2]);
-                            F[k][t][3] = BIOIK_FMA(d[k], D3, F[k][t][3]);
-                            F[k][t][4] = BIOIK_FMA(d[k], D4, F[k][t][4]);
-                            F[k][t][5] = BIOIK_FMA(d[k], D5, F[k][t][5]);
-                            F[k][t][6] = BIOIK_FMA(d[k], D6, F[k][t][6]);
-                        }
-                    }
+                        for(int j = 0; j < 7; j++) F[k][t][j] = BIOIK_FMA(d[k], Dv[j], FIRST ? s_tip0[8 * t + j] : F[k][t][j]);
                 }
                 dp += 8;
                 if(JOINT)
@@ -461,7 +449,10 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
                             for(int k = 0; k < CH; k++) joint_goal_accumulate(jg_type[j], jg_var[j], i, x[k], hi, mid, halfspan, vw, seedv, p0, acc[k][j]);
                         }
                 }
-            }
+            };
+            gene_step(std::true_type{}, 0);
+#pragma unroll 1
+            for(int i = 1; i < n; i++) gene_step(std::false_type{}, i);
 
             // fitness: weighted sum in goal order (src/problem.cpp:251-257)
 #pragma unroll
@@ -619,36 +610,34 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
             f_par1 = nf1;
         }
 
-        // ---- new parents into the other buffer (lanes 0/1 re-derive the winners) -------------------
+        // ---- new parents into the other buffer: lane i re-derives gene i of both winners --------------
         double* nxt = s_par + (cur ^ 1) * 4 * n;
-        if(lane < 2)
         {
-            const int wc = (lane == 0) ? (int)w1_child : (int)w2_child;
-            double* og = nxt + lane * n;        // genes of individuals[lane]
-            double* ogr = nxt + (2 + lane) * n; // gradients
-            if(wc < 2)
+            const int wc1 = (int)w1_child, wc2 = (int)w2_child;
+            for(int i = lane; i < n; i += 32)
             {
-                const double* sg = wc == 0 ? p_g0 : p_g1;
-                const double* sgr = wc == 0 ? p_gr0 : p_gr1;
-                for(int i = 0; i < n; i++)
+                const double g0 = p_g0[i], lo = s_rec[4 * i + 2], hi = s_rec[4 * i + 3];
+#pragma unroll
+                for(int w = 0; w < 2; w++)
                 {
-                    og[i] = sg[i];
-                    ogr[i] = sgr[i];
-                }
-            }
-            else
-            {
-                const int wpar = wc & 1; // 1 = odd child
-                const int col = (wpar ? 3 : 0) + (wc % 3);
-                for(int i = 0; i < n; i++)
-                {
-                    double g0 = p_g0[i];
-                    double gene = g0;
-                    gene += BIOIK_LDG(mt + (size_t)i * R + (wc - 2));
-                    gene += s_term[6 * i + col];
-                    gene = clampd(gene, s_rec[4 * i + 2], s_rec[4 * i + 3]);
-                    og[i] = gene;
-                    ogr[i] = mix(s_pg[wpar * n + i], gene - g0, 0.3); // :299
+                    const int wc = w ? wc2 : wc1;
+                    double gene, gr;
+                    if(wc < 2)
+                    {
+                        gene = wc == 0 ? g0 : p_g1[i];
+                        gr = wc == 0 ? p_gr0[i] : p_gr1[i];
+                    }
+                    else
+                    {
+                        const int wpar = wc & 1; // 1 = odd child
+                        gene = g0;
+                        gene += BIOIK_LDG(mt + (size_t)i * R + (wc - 2));
+                        gene += s_term[6 * i + (wpar ? 3 : 0) + (wc % 3)];
+                        gene = clampd(gene, lo, hi);
+                        gr = mix(s_pg[wpar * n + i], gene - g0, 0.3); // :299
+                    }
+                    nxt[w * n + i] = gene;      // genes of individuals[w]
+                    nxt[(2 + w) * n + i] = gr;  // gradients
                 }
             }
         }

@@ -36,23 +36,36 @@ struct SerialPlan
 
 __host__ __device__ inline int serial_fixed_doubles(const DProblem& P) { return 4 * P.n /*ind,temp,grad,stash*/ + 3 * 7 * P.T /*ph2,ph3,tip0*/ + P.n /*base*/ + GOAL_NPARAM * P.G + P.n_vars; }
 
-inline SerialPlan make_serial_plan(const DProblem& P, size_t smem_limit = 200 * 1024)
+// The kernel is latency-bound (one dependent chain per thread), so what matters is that ALL tasks are
+// resident at once (a second wave doubles the time): blocks of one warp pack best; pick the most
+// on-chip variant whose resident threads per SM cover ceil(tasks / SMs).
+inline SerialPlan make_serial_plan(const DProblem& P, int tasks = 0, int sm_count = 148, size_t smem_per_sm = 227 * 1024)
 {
-    SerialPlan pl;
     const int fixed = serial_fixed_doubles(P), dl = 7 * P.T * P.n, fr = 7 * P.L;
-    const int blocks[] = {128, 64, 32};
-    for(int variant = 0; variant < 3; variant++) // 0: everything on chip, 1: delta in HBM state, 2: frames local too
-        for(int b : blocks)
+    const int need = tasks > 0 ? (tasks + sm_count - 1) / sm_count : 64; // threads per SM for a single wave
+    SerialPlan best;
+    int best_resident = -1;
+    const int variants[4][2] = {{1, 1}, {1, 0}, {0, 1}, {0, 0}}; // {delta on chip, frames on chip}
+    for(int v = 0; v < 4; v++)
+    {
+        SerialPlan pl;
+        pl.block = 32;
+        pl.delta_smem = variants[v][0];
+        pl.frames_smem = variants[v][1];
+        pl.per_thread = fixed + (pl.delta_smem ? dl : 0) + (pl.frames_smem ? fr : 0);
+        pl.smem_bytes = (size_t)pl.per_thread * pl.block * sizeof(double);
+        if(pl.smem_bytes + 1024 > smem_per_sm) continue;
+        int blocks = (int)(smem_per_sm / (pl.smem_bytes + 1024)); // 1 KB reserved per resident block
+        if(blocks > 32) blocks = 32;
+        const int resident = blocks * pl.block;
+        if(resident >= need) return pl; // most on-chip variant that still runs in one wave
+        if(resident > best_resident)
         {
-            pl.block = b;
-            pl.delta_smem = variant < 1;
-            pl.frames_smem = variant < 2;
-            pl.per_thread = fixed + (pl.delta_smem ? dl : 0) + (pl.frames_smem ? fr : 0);
-            pl.smem_bytes = (size_t)pl.per_thread * b * sizeof(double);
-            // want at least 64 resident threads per SM for the on-chip variants
-            if(pl.smem_bytes * (b < 64 ? 2 : 1) <= smem_limit) return pl;
+            best_resident = resident;
+            best = pl;
         }
-    return pl; // 32 threads, delta + frames off chip: always fits (fixed part <= ~1 KB/thread)
+    }
+    return best;
 }
 
 template <class AF, class AT> BIOIK_HD void copy_tips(const DProblem& P, AF frames, AT tips)

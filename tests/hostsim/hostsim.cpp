@@ -216,6 +216,12 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     {
         // production launch sequence of enqueue_solve(): k_evolve_fast + the fused k_serial (32-thread blocks here)
         SerialPlan pl = make_serial_plan(P);
+        if(use_fast >= 2)
+        {
+            // forced placement variant of the serial kernel: 2 = all on chip, 3 = frames local, 4 = delta in HBM, 5 = both off chip
+            pl.delta_smem = (use_fast == 2 || use_fast == 3);
+            pl.frames_smem = (use_fast == 2 || use_fast == 4);
+        }
         pl.block = 32;
         SerialKernel ks = select_serial(pl);
         const int sgrid = (2 * B + 31) / 32;

@@ -102,3 +102,16 @@ def test_mixed_goals_fast_kernel(sim, oracle):
         b = sim.solve(rm, pr, cfg, None, seeds, rs, 3, fast=fast)
         for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
             assert np.array_equal(a[k], b[k]), (k, fast)
+
+
+@pytest.mark.parametrize("variant", [2, 3, 4, 5])
+def test_serial_kernel_placement_variants(sim, oracle, variant):
+    """The fused serial kernel keeps delta frames / link frames in shared memory, in the HBM state or in local
+    memory depending on what fits (make_serial_plan): every placement gives the same bits."""
+    for name, B, pop, steps in (("cfg3", 2, 36, 3), ("cfg4", 2, 36, 2)):
+        w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+        cfg = oracle_lib.make_cfg(population=pop)
+        a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+        b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, fast=variant)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+            assert np.array_equal(a[k], b[k]), (name, k)
