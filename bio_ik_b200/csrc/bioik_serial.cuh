@@ -366,7 +366,9 @@ typedef void (*SerialKernel)(const DProblem, DState, int, int);
 
 inline SerialKernel select_serial(const SerialPlan& pl)
 {
-#define BIOIK_SER(BS) (pl.delta_smem ? (SerialKernel)k_serial<BS, true, true> : (pl.frames_smem ? (SerialKernel)k_serial<BS, false, true> : (SerialKernel)k_serial<BS, false, false>))
+#define BIOIK_SER(BS)                                                                                                            \
+    (pl.delta_smem ? (pl.frames_smem ? (SerialKernel)k_serial<BS, true, true> : (SerialKernel)k_serial<BS, true, false>) \
+                   : (pl.frames_smem ? (SerialKernel)k_serial<BS, false, true> : (SerialKernel)k_serial<BS, false, false>))
     switch(pl.block)
     {
     case 128: return BIOIK_SER(128);
