@@ -36,6 +36,9 @@ struct bioik_ctx
     BioikSolverCfg cfg;
     HostRobot robot;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_evolve = nullptr, stream_serial = nullptr; // internal streams of the two-half pipeline
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_evolve[2] = {nullptr, nullptr}, ev_serial[2] = {nullptr, nullptr};
+    bool pipeline = true; // BIOIK_NO_PIPELINE=1 disables the two-half overlap
     std::string error;
     int64_t launches = 0;
 
@@ -225,6 +228,32 @@ int check_launch(bioik_ctx* ctx, const char* what)
     return BIOIK_OK;
 }
 
+// view of queries [q0, q0 + nq) of a batch state
+DState slice_state(const DState& S, const DProblem& P, int q0, int nq)
+{
+    DState H = S;
+    const size_t q = (size_t)q0, n = P.n, T = P.T, G = P.G;
+    H.B = nq;
+    H.goal_params += q * G * GOAL_NPARAM;
+    H.seeds += q * P.n_vars;
+    H.rng_seeds += q;
+    H.genes += q * 4 * n;
+    H.grads += q * 4 * n;
+    H.sfit += q * 2;
+    H.impr += q * 2;
+    H.sol += q * n;
+    H.solfit += q;
+    H.rng += q;
+    H.done += q;
+    H.steps += q;
+    H.success += q;
+    H.ccount += q * 2 * S.gens;
+    H.base += q * 2 * n;
+    H.tip0 += q * 2 * T * 7;
+    H.delta += q * 2 * T * n * 7;
+    return H;
+}
+
 // enqueue a whole solve on `st`; all pointers are device pointers
 int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
 {
@@ -281,39 +310,69 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     if((rc = check_launch(ctx, "k_init")) != BIOIK_OK) return rc;
     if(!ctx->force_generic)
     {
-        // production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial
-        ctx->splan = make_serial_plan(P, 2 * B, ctx->sm_count);
+        // Production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial.
+        // The batch is cut in two halves that ping-pong between two internal streams, so the latency-bound serial
+        // kernel of one half runs in the shadow of the throughput-bound generation kernel of the other half.
+        const int H = (B >= 2048 && ctx->pipeline) ? 2 : 1;
+        int q0[3] = {0, H == 2 ? (B / 2) : B, B};
+        DState Sh[2];
+        for(int h = 0; h < H; h++) Sh[h] = slice_state(S, P, q0[h], q0[h + 1] - q0[h]);
+        ctx->splan = make_serial_plan(P, 2 * Sh[0].B, ctx->sm_count);
         ctx->serial = select_serial(ctx->splan);
         const SerialPlan& pl = ctx->splan;
         if(pl.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        const int sgrid = (2 * B + pl.block - 1) / pl.block;
-        if(steps > 0)
+        cudaStream_t se = st, ss = st;
+        if(H == 2)
         {
-            EventPair s0 = get_pair(ctx, 1);
-            cudaEventRecord(s0.a, st);
-            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, 0, PH_PREPARE);
-            if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
-            cudaEventRecord(s0.b, st);
-            ctx->pending.push_back(s0);
+            se = ctx->stream_evolve, ss = ctx->stream_serial;
+            CU(ctx, cudaEventRecord(ctx->ev_fork, st));
+            CU(ctx, cudaStreamWaitEvent(se, ctx->ev_fork, 0));
+            CU(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         }
-        for(int step = 0; step < steps; step++)
-        {
+        auto launch_serial = [&](int h, int step, int phases) -> int {
+            const int sgrid = (2 * Sh[h].B + pl.block - 1) / pl.block;
+            EventPair sp = get_pair(ctx, 1);
+            cudaEventRecord(sp.a, ss);
+            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, phases);
+            int r = check_launch(ctx, "k_serial");
+            cudaEventRecord(sp.b, ss);
+            ctx->pending.push_back(sp);
+            if(H == 2) cudaEventRecord(ctx->ev_serial[h], ss);
+            return r;
+        };
+        auto launch_evolve = [&](int h, int step) -> int {
+            const int eb = (2 * Sh[h].B + warps_per_block - 1) / warps_per_block;
+            if(H == 2) cudaStreamWaitEvent(se, ctx->ev_serial[h], 0);
             EventPair ev = get_pair(ctx, 0);
-            cudaEventRecord(ev.a, st);
+            cudaEventRecord(ev.a, se);
             if(fast)
-                fast<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step, ctx->d_mtab);
+                fast<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step, ctx->d_mtab);
             else
-                k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
-            if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
-            cudaEventRecord(ev.b, st);
+                k_evolve<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step);
+            int r = check_launch(ctx, "k_evolve");
+            cudaEventRecord(ev.b, se);
             ctx->pending.push_back(ev);
-            EventPair s2 = get_pair(ctx, 1);
-            cudaEventRecord(s2.a, st);
-            const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
-            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, phases);
-            if((rc = check_launch(ctx, "k_serial")) != BIOIK_OK) return rc;
-            cudaEventRecord(s2.b, st);
-            ctx->pending.push_back(s2);
+            if(H == 2) cudaEventRecord(ctx->ev_evolve[h], se);
+            return r;
+        };
+        if(steps > 0)
+            for(int h = 0; h < H; h++)
+                if((rc = launch_serial(h, 0, PH_PREPARE)) != BIOIK_OK) return rc;
+        for(int step = 0; step < steps; step++)
+            for(int h = 0; h < H; h++)
+            {
+                if((rc = launch_evolve(h, step)) != BIOIK_OK) return rc;
+                if(H == 2) cudaStreamWaitEvent(ss, ctx->ev_evolve[h], 0);
+                const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
+                if((rc = launch_serial(h, step, phases)) != BIOIK_OK) return rc;
+            }
+        if(H == 2)
+        {
+            // join: the caller's stream continues after both halves are done
+            CU(ctx, cudaEventRecord(ctx->ev_join[0], ss));
+            CU(ctx, cudaEventRecord(ctx->ev_join[1], se));
+            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
+            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
         }
     }
     else
@@ -398,6 +457,16 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     }
     cudaError_t e = cudaSetDevice(cfg->device);
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess)
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi = numerically lowest = highest priority
+        e = cudaStreamCreateWithPriority(&ctx->stream_evolve, cudaStreamNonBlocking, lo);
+        if(e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream_serial, cudaStreamNonBlocking, hi);
+        cudaEvent_t* evs[] = {&ctx->ev_fork, &ctx->ev_join[0], &ctx->ev_join[1], &ctx->ev_evolve[0], &ctx->ev_evolve[1], &ctx->ev_serial[0], &ctx->ev_serial[1]};
+        for(auto* pe : evs)
+            if(e == cudaSuccess) e = cudaEventCreateWithFlags(pe, cudaEventDisableTiming);
+    }
     if(e == cudaSuccess) e = cudaMalloc(&ctx->d_uniform, sizeof(double) * 1024 * 1024 * 8);
     if(e == cudaSuccess) e = cudaMalloc(&ctx->d_gauss, sizeof(double) * 1024 * 1024 * 8);
     if(e == cudaSuccess) e = cudaMalloc(&ctx->dP, sizeof(DProblem));
@@ -419,6 +488,8 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     {
         const char* fg = getenv("BIOIK_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
+        const char* np = getenv("BIOIK_NO_PIPELINE");
+        ctx->pipeline = !(np && np[0] == '1');
     }
     *out = ctx;
     return BIOIK_OK;
@@ -428,12 +499,16 @@ void bioik_destroy(bioik_ctx* ctx)
 {
     if(!ctx) return;
     cudaSetDevice(ctx->cfg.device);
-    if(ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for(auto& p : ctx->pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
+    if(ctx->stream_evolve) cudaStreamDestroy(ctx->stream_evolve);
+    if(ctx->stream_serial) cudaStreamDestroy(ctx->stream_serial);
+    for(cudaEvent_t ev : {ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1], ctx->ev_evolve[0], ctx->ev_evolve[1], ctx->ev_serial[0], ctx->ev_serial[1]})
+        if(ev) cudaEventDestroy(ev);
     delete ctx;
 }
 
