@@ -38,7 +38,8 @@ struct bioik_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t stream_evolve = nullptr, stream_serial = nullptr; // internal streams of the two-half pipeline
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_evolve[2] = {nullptr, nullptr}, ev_serial[2] = {nullptr, nullptr};
-    bool pipeline = true; // BIOIK_NO_PIPELINE=1 disables the two-half overlap
+    int ch_cap = 8; // BIOIK_EVOLVE_CH: cap of the register block of k_evolve_fast (experiments)
+    bool pipeline = false; // BIOIK_PIPELINE=1 enables the two-half overlap (experimental)
     std::string error;
     int64_t launches = 0;
 
@@ -290,7 +291,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
     const int warps_per_block = 4;
-    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C);
+    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap);
     size_t smem;
     if(fast)
     {
@@ -488,8 +489,10 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     {
         const char* fg = getenv("BIOIK_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
-        const char* np = getenv("BIOIK_NO_PIPELINE");
-        ctx->pipeline = !(np && np[0] == '1');
+        const char* ch = getenv("BIOIK_EVOLVE_CH");
+        if(ch && atoi(ch) > 0) ctx->ch_cap = atoi(ch);
+        const char* np = getenv("BIOIK_PIPELINE"); // measured slower than the plain sequence on B200 (wave quantisation of the half grids): opt-in
+        ctx->pipeline = np && np[0] == '1';
     }
     *out = ctx;
     return BIOIK_OK;

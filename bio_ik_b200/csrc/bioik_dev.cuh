@@ -333,6 +333,31 @@ template <class AF> BIOIK_HD F7 delta_frame(const DProblem& P, AF frames, int ge
 
 // computeApproximateMutations for one genotype, src/forward_kinematics.h:1061-1110 (AVX+FMA form).
 // tip0 [T][7], delta [T][n][7] (zero where unmasked), base [n], x [n] -> out [T][7]
+// Same, skipping (tip, gene) pairs that are structurally independent (DGene::tipmask): their delta frame is
+// all-zero, and fma(d, 0, f) == f, so the result is unchanged.
+template <class A0, class AD, class AB, class AX, class AO> BIOIK_HD void approx_frames_sparse(const DProblem& P, A0 tip0, AD delta, AB base, AX x, AO out)
+{
+    const int T = P.T, n = P.n;
+    for(int t = 0; t < T; t++)
+    {
+        double f0 = tip0[7 * t + 0], f1 = tip0[7 * t + 1], f2 = tip0[7 * t + 2], f3 = tip0[7 * t + 3], f4 = tip0[7 * t + 4], f5 = tip0[7 * t + 5], f6 = tip0[7 * t + 6];
+        AD D = delta + t * n * 7;
+        for(int i = 0; i < n; i++)
+        {
+            if(!((P.genes[i].tipmask >> t) & 1)) continue;
+            double d = x[i] - base[i]; // :1086
+            f0 = BIOIK_FMA(d, D[7 * i + 0], f0);
+            f1 = BIOIK_FMA(d, D[7 * i + 1], f1);
+            f2 = BIOIK_FMA(d, D[7 * i + 2], f2);
+            f3 = BIOIK_FMA(d, D[7 * i + 3], f3);
+            f4 = BIOIK_FMA(d, D[7 * i + 4], f4);
+            f5 = BIOIK_FMA(d, D[7 * i + 5], f5);
+            f6 = BIOIK_FMA(d, D[7 * i + 6], f6);
+        }
+        out[7 * t + 0] = f0; out[7 * t + 1] = f1; out[7 * t + 2] = f2; out[7 * t + 3] = f3; out[7 * t + 4] = f4; out[7 * t + 5] = f5; out[7 * t + 6] = f6;
+    }
+}
+
 template <class A0, class AD, class AB, class AX, class AO> BIOIK_HD void approx_frames(int T, int n, A0 tip0, AD delta, AB base, AX x, AO out)
 {
     for(int t = 0; t < T; t++)

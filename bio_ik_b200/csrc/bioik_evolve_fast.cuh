@@ -511,14 +511,15 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
                 else if(c < C)
                 {
                     // running top-2 of this lane; position == child slot without pre-selection
+                    // a lane meets its children in increasing position order, so ties keep the earlier one: strict < only
                     uint64_t kk = fast_fitness_key(prim);
                     uint32_t pk = (uint32_t)c * 512u + (uint32_t)c;
-                    if(key_less(kk, pk, k1, q1))
+                    if(kk < k1)
                     {
                         k2 = k1; q2 = q1;
                         k1 = kk; q1 = pk;
                     }
-                    else if(key_less(kk, pk, k2, q2))
+                    else if(kk < k2)
                     {
                         k2 = kk; q2 = pk;
                     }
@@ -658,13 +659,14 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
 typedef void (*EvolveFastKernel)(const DProblem*, DState, int, const double*);
 
 // picks the instantiation for (tips, population, goals); returns nullptr if the generic kernel must be used
-inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C)
+inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap = 8)
 {
     const int T = P.T;
     if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
     const bool J = P.n_joint_goals > 0;
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);
-    const int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
+    int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
+    if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
 #define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
     if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
     switch(T)

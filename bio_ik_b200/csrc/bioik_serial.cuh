@@ -190,7 +190,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
                 if(single)
                     approx_frames1(T, n, delta, e - 1, dp, CSC(ph2), ph3); // :469
                 else
-                    approx_frames(T, n, CSC(tip0), delta, CSC(base), CSC(temp), out); // :462,:487,:494,:526
+                    approx_frames_sparse(P, CSC(tip0), delta, CSC(base), CSC(temp), out); // :462,:487,:494,:526
                 // fitness: primary + secondary (computeCombinedFitnessActiveVariables, src/ik_base.h:179-185)
                 const double prim = goal_fitness_t(P, 0, cgp, CSC(out), CSC(temp), seed);
                 double comb = prim;
@@ -352,8 +352,15 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         for(int t = 0; t < T; t++)
             for(int i = 0; i < n; i++)
             {
-                bool masked;
-                store_frame(d0 + ((size_t)t * n + i) * 7, delta_frame(P, frames, i, t, masked));
+                F7 df;
+                if((P.genes[i].tipmask >> t) & 1)
+                {
+                    bool masked;
+                    df = delta_frame(P, frames, i, t, masked);
+                }
+                else // structurally independent pair: the Jacobian column is exactly zero (:609-617), so is the delta frame
+                    df = F7{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+                store_frame(d0 + ((size_t)t * n + i) * 7, df);
             }
     }
 }
