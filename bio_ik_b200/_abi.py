@@ -84,7 +84,7 @@ def uptr(a):
 
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(REPO_ROOT, "bio_ik_b200", "csrc", "libbioik_b200.so")
+LIB_PATH = os.environ.get("BIOIK_LIB") or os.path.join(REPO_ROOT, "bio_ik_b200", "csrc", "libbioik_b200.so")  # BIOIK_LIB: alternative build (experiments)
 
 # every symbol include/bioik_b200.h declares
 ABI_SYMBOLS = [

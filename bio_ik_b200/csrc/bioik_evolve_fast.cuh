@@ -217,6 +217,9 @@ __device__ __forceinline__ uint64_t fast_fitness_key(double f) { return (f != f)
 constexpr uint64_t FAST_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
 __device__ __forceinline__ bool key_less(uint64_t ka, uint32_t pa, uint64_t kb, uint32_t pb) { return ka < kb || (ka == kb && pa < pb); }
 
+#ifndef BIOIK_EVOLVE_MINBLOCKS
+#define BIOIK_EVOLVE_MINBLOCKS 4
+#endif
 constexpr int FAST_MAX_CPL = 8; // population <= 256
 
 // fitness of one genotype under the task's approximator, by a single lane (parents at the start of a step)
@@ -272,7 +275,7 @@ __device__ __forceinline__ double fast_eval_one(const DProblem& P, int n, const 
 // T = tips, CH = children evaluated together per lane (register block),
 // GSPEC = 1: the problem is exactly one primary PoseGoal (the plugin's default goal for a one-tip group);
 // JOINT: joint-space goals present (accumulated in the gene loop)
-template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds__(128, (T * CH <= 4 ? 4 : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;

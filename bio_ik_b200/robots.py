@@ -154,3 +154,26 @@ def random_tree(seed=0, n_joints=9, branch_at=4, prismatic_every=4):
     rm = RobotModel(f"random_tree{seed}", links)
     groups = {"all": JointModelGroup(rm, "all", joints, [trunk[-1], prev])}
     return rm, groups
+
+
+def mimic_gripper_arm():
+    """4-DOF arm with a two-finger gripper whose second finger MIMICS the first (factor -1.5, offset 0.01) and a
+    second mimic chained on it: exercises updateMimic, the mimic branches of the Jacobian (joint_dependencies, scale
+    products) and a goal on a link below a mimic joint (src/forward_kinematics.h:230-246,581-587,623-630)."""
+    links = [
+        Link("base", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("l1", "base", JOINT_REVOLUTE, xyz=(0, 0, 0.3), axis=(0, 0, 1), lower=-2.5, upper=2.5, velocity=2.0, joint_name="j1"),
+        Link("l2", "l1", JOINT_REVOLUTE, xyz=(0.1, 0, 0.2), rpy=(0.3, 0, 0), axis=(0, 1, 0), lower=-1.8, upper=1.8, velocity=2.0, joint_name="j2"),
+        Link("l3", "l2", JOINT_REVOLUTE, xyz=(0.35, 0, 0), axis=(0, 1, 0), lower=-2.2, upper=2.2, velocity=3.0, joint_name="j3"),
+        Link("l4", "l3", JOINT_PRISMATIC, xyz=(0.3, 0, 0), rpy=(0, 0.2, 0.1), axis=(1, 0, 0), lower=0.0, upper=0.15, velocity=0.5, joint_name="j4"),
+        Link("finger_a", "l4", JOINT_REVOLUTE, xyz=(0.05, 0.03, 0), axis=(0, 0, 1), lower=-0.1, upper=0.8, velocity=1.0, joint_name="finger_a_joint"),
+        Link("finger_b", "l4", JOINT_REVOLUTE, xyz=(0.05, -0.03, 0), axis=(0, 0, 1), lower=-1.3, upper=0.2, velocity=1.0, joint_name="finger_b_joint", mimic="finger_a_joint",
+             mimic_factor=-1.5, mimic_offset=0.01),
+        Link("finger_b_tip", "finger_b", JOINT_REVOLUTE, xyz=(0.04, 0, 0), axis=(0, 0, 1), lower=-1.0, upper=1.0, velocity=1.0, joint_name="finger_b_tip_joint", mimic="finger_b_joint",
+             mimic_factor=0.5, mimic_offset=0.0),
+        Link("pad_a", "finger_a", JOINT_FIXED, xyz=(0.04, 0, 0), joint_name="pad_a_joint"),
+        Link("pad_b", "finger_b_tip", JOINT_FIXED, xyz=(0.03, 0, 0), joint_name="pad_b_joint"),
+    ]
+    rm = RobotModel("mimic_gripper_arm", links)
+    groups = {"all": JointModelGroup(rm, "all", ["j1", "j2", "j3", "j4", "finger_a_joint", "finger_b_joint", "finger_b_tip_joint"], ["pad_a", "pad_b"])}
+    return rm, groups

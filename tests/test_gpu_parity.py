@@ -24,7 +24,7 @@ def ofk(oracle):
 # rows a9-a11, a6, a7 of SURVEY.md §8(a): exact FK, Jacobian/approximator, approximate fitness
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("maker,group", [(robots.pr2_like, "all"), (robots.pr2_like, "right_arm"), (robots.snake, "all"), (robots.shadow_like_hand, "hand"),
-                                         (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all")])
+                                         (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all"), (robots.mimic_gripper_arm, "all")])
 def test_exact_fk_and_delta_frames(oracle, maker, group):
     rm, groups = maker()
     g = groups[group]
@@ -263,3 +263,20 @@ def test_mixed_goal_problem_on_gpu(oracle):
     ref = oracle.solve(rm, pr, cfg, None, seeds, rs, 8)
     solver = IKSolver(rm, population=45).initialize(pr)
     gpu_util.assert_bit_equal(solver.trace(None, seeds, rs, 8), ref)
+
+
+def test_mimic_joints_on_gpu(oracle):
+    rm, groups = robots.mimic_gripper_arm()
+    pr = Problem().initialize(rm, groups["all"], [G.PositionGoal("pad_a"), G.PoseGoal("pad_b")])
+    rng = np.random.default_rng(1)
+    B = 48
+    tg = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    tips = oracle.fk(rm, pr, tg)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    gp[:, 0, 0:3], gp[:, 1, 0:7] = tips[:, 0, 0:3], tips[:, 1, :]
+    cfg = oracle_lib.make_cfg(population=64)
+    rs = np.arange(B, dtype=np.uint32) + 1
+    ref = oracle.solve(rm, pr, cfg, gp, seeds, rs, 12)
+    solver = IKSolver(rm, population=64).initialize(pr)
+    gpu_util.assert_bit_equal(solver.trace(gp, seeds, rs, 12), ref)

@@ -115,3 +115,25 @@ def test_serial_kernel_placement_variants(sim, oracle, variant):
         b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, fast=variant)
         for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
             assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_mimic_joints(sim, oracle):
+    """updateMimic + the mimic branches of the Jacobian (chained mimic joints, two tips below them)."""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.mimic_gripper_arm()
+    pr = Problem().initialize(rm, groups["all"], [G.PositionGoal("pad_a"), G.PoseGoal("pad_b")])
+    assert [rm.variable_names[i] for i in pr.active_variables] == ["j1", "j2", "j3", "j4", "finger_a_joint"]  # mimic joints are not genes
+    rng = np.random.default_rng(1)
+    tg = workloads.sample_configurations(rm, pr.active_variables, 3, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 3, rng)
+    tips = oracle.fk(rm, pr, tg)
+    gp = np.repeat(pr.default_goal_params()[None], 3, 0)
+    gp[:, 0, 0:3], gp[:, 1, 0:7] = tips[:, 0, 0:3], tips[:, 1, :]
+    cfg = oracle_lib.make_cfg(population=40)
+    rs = np.arange(3, dtype=np.uint32) + 1
+    a = oracle.solve(rm, pr, cfg, gp, seeds, rs, 5)
+    for fast in (0, 1):
+        b = sim.solve(rm, pr, cfg, gp, seeds, rs, 5, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(a[k], b[k]), (k, fast)

@@ -108,6 +108,10 @@ def test_det_sincos_accuracy(oracle):
 def numpy_fk(robot, variables):
     """Independent exact FK (scipy rotations), returns link frames [L][7]."""
     a = robot.arrays
+    variables = np.array(variables, dtype=float)
+    for l, link in enumerate(robot.links):  # mimic joints follow their source joint
+        if link.mimic:
+            variables[a["joint_first_var"][l]] = variables[a["joint_first_var"][robot.joint_index[link.mimic]]] * link.mimic_factor + link.mimic_offset
     frames = []
     for l, link in enumerate(robot.links):
         o = a["link_origin"][l]
@@ -129,7 +133,7 @@ def numpy_fk(robot, variables):
     return frames
 
 
-@pytest.mark.parametrize("maker", [robots.pr2_like, robots.snake, robots.shadow_like_hand, lambda: robots.random_tree(3)])
+@pytest.mark.parametrize("maker", [robots.pr2_like, robots.snake, robots.shadow_like_hand, lambda: robots.random_tree(3), robots.mimic_gripper_arm])
 def test_exact_fk_vs_independent_numpy(oracle, maker):
     rm, groups = maker()
     g = list(groups.values())[-1]
@@ -156,7 +160,7 @@ def body_twist(fc, f0, f1, h):
     return np.concatenate([v, w])
 
 
-@pytest.mark.parametrize("maker", [robots.pr2_like, lambda: robots.random_tree(4)])
+@pytest.mark.parametrize("maker", [robots.pr2_like, lambda: robots.random_tree(4), robots.mimic_gripper_arm])
 def test_jacobian_vs_central_differences(oracle, maker):
     """computeJacobian (src/forward_kinematics.h:600-730) = tip-local twist per unit variable change."""
     rm, groups = maker()
