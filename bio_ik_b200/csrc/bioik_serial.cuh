@@ -12,6 +12,7 @@
 #pragma once
 
 #include "bioik_dev.cuh"
+#include "bioik_evolve_fast.cuh" // link_goal_value
 
 #ifdef BIOIK_HOSTSIM
 #define BIOIK_PROBLEM_PARAM const DProblem& P
@@ -145,6 +146,90 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         double dp = 0.0000001;                                                                                // :450
         if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
         const bool quad = S.memetic == 'q';
+        // Fast path for the plugin's default problem (exactly one primary PoseGoal, one tip): tip frames and goal
+        // parameters stay in registers; the Pose goal does not read the genes, so the n one-variable evaluations
+        // reduce to 7 FMAs + the goal.  Same operations in the same order as the general loop below.
+        const bool single_pose = (G == 1 && T == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary);
+        if(single_pose)
+        {
+            double pg[8], t0r[7];
+#pragma unroll
+            for(int k = 0; k < 8; k++) pg[k] = gp[k];
+#pragma unroll
+            for(int k = 0; k < 7; k++) t0r[k] = tip0[k];
+            const double wsq = P.goals[0].weight_sq;
+            auto full_frames = [&](double (&F)[7]) {
+#pragma unroll
+                for(int k = 0; k < 7; k++) F[k] = t0r[k];
+                for(int i = 0; i < n; i++)
+                {
+                    if(!(P.genes[i].tipmask & 1)) continue;
+                    const double d = temp[i] - base[i]; // :1086
+                    const DeltaCol D = delta + 7 * i;
+#pragma unroll
+                    for(int k = 0; k < 7; k++) F[k] = BIOIK_FMA(d, D[k], F[k]);
+                }
+            };
+            auto pose = [&](const double (&F)[7]) { return 0.0 + link_goal_value(G_POSE, pg, F) * wsq; }; // sum = 0.0; sum += e * weight_sq
+            for(int generation = 0; generation < S.memetic_iters; generation++)
+            {
+                double F2[7], F3[7];
+                for(int i = 0; i < n; i++) temp[i] = ind[i]; // :460
+                full_frames(F2);                               // :462
+                const double f2p = pose(F2);                   // :463
+                const double fa = f2p + 0.0;                   // :464 (no secondary goals)
+                for(int i = 0; i < n; i++)                     // :465-474
+                {
+                    const DeltaCol D = delta + 7 * i;
+#pragma unroll
+                    for(int k = 0; k < 7; k++) F3[k] = BIOIK_FMA(dp, D[k], F2[k]); // :469
+                    double fb = 0.0;
+                    fb += pose(F3);
+                    fb += 0.0;
+                    grad[i] = fb - fa;
+                }
+                double sum = dp * dp; // :477-482
+                for(int i = 0; i < n; i++) sum += BIOIK_FABS(grad[i]);
+                const double f = 1.0 / sum * dp;
+                for(int i = 0; i < n; i++) grad[i] *= f;
+                for(int i = 0; i < n; i++) temp[i] = ind[i] - grad[i]; // :485-488
+                full_frames(F3);
+                double f1 = 0.0;
+                f1 += pose(F3);
+                f1 += 0.0;
+                const double f2 = fa;
+                for(int i = 0; i < n; i++) temp[i] = ind[i] + grad[i]; // :492-495
+                full_frames(F3);
+                double f3 = 0.0;
+                f3 += pose(F3);
+                f3 += 0.0;
+                if(quad) // :502-506,:525
+                {
+                    double v1 = (f2 - f1);
+                    double v2 = (f3 - f2);
+                    double v = (v1 + v2) * 0.5;
+                    double a = (v1 - v2);
+                    double step_size = v / a;
+                    for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] + grad[i] * step_size * 1.0, P.genes[i].clip_min, P.genes[i].clip_max);
+                }
+                else // :549-554
+                {
+                    double cost_diff = (f3 - f1) * 0.5;
+                    double step_size = f2 / cost_diff;
+                    for(int i = 0; i < n; i++) temp[i] = clampd(ind[i] - grad[i] * step_size, P.genes[i].clip_min, P.genes[i].clip_max);
+                }
+                full_frames(F2); // :526 / :555
+                const double f4p = pose(F2);
+                if(f4p < f2p) // :530-538 / :559-567
+                {
+                    for(int i = 0; i < n; i++) ind[i] = temp[i];
+                    continue;
+                }
+                else
+                    break;
+            }
+        }
+        else
         for(int generation = 0; generation < S.memetic_iters; generation++)
         {
             double f2p = 0.0, fa = 0.0, f1 = 0.0, f3 = 0.0, f4p = 0.0;
