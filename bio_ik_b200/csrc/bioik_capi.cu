@@ -70,7 +70,14 @@ struct bioik_ctx
     int32_t *d_osucc = nullptr, *d_osteps = nullptr;
     double* d_default_gp = nullptr; // [G][NPARAM] defaults (goal_params == NULL)
 
-    // timing
+    // timing (collected only after bioik_kernel_time has been called once: events cost host time per launch)
+    bool timing = false;
+    bool capturing = false;
+    // CUDA graph of the last host-API solve shape (B, steps, early_exit, with/without per-query goal parameters)
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_B = -1, graph_steps = -1, graph_early = -1, graph_gp = -1;
+    int64_t graph_launches = 0;
+    bool use_graphs = true; // BIOIK_NO_GRAPH=1 disables
     std::vector<EventPair> pending, pool;
     double ms_evolve = 0, ms_serial = 0;
     int64_t n_evolve = 0, n_serial = 0;
@@ -198,6 +205,16 @@ int ensure_schedules(bioik_ctx* ctx, int steps)
     return BIOIK_OK;
 }
 
+struct Timed // records an event pair around a launch when timing is on (and not while capturing a graph)
+{
+    bioik_ctx* ctx;
+    cudaStream_t st;
+    EventPair p;
+    bool on;
+    Timed(bioik_ctx* c, cudaStream_t s, int kind);
+    void done();
+};
+
 EventPair get_pair(bioik_ctx* ctx, int kind)
 {
     EventPair p;
@@ -217,6 +234,23 @@ EventPair get_pair(bioik_ctx* ctx, int kind)
 
 void drain_events(bioik_ctx* ctx);
 
+Timed::Timed(bioik_ctx* c, cudaStream_t s, int kind) : ctx(c), st(s), on(c->timing && !c->capturing)
+{
+    if(on)
+    {
+        p = get_pair(ctx, kind);
+        cudaEventRecord(p.a, st);
+    }
+}
+void Timed::done()
+{
+    if(on)
+    {
+        cudaEventRecord(p.b, st);
+        ctx->pending.push_back(p);
+    }
+}
+
 int check_launch(bioik_ctx* ctx, const char* what)
 {
     cudaError_t e = cudaGetLastError();
@@ -227,6 +261,12 @@ int check_launch(bioik_ctx* ctx, const char* what)
     }
     ctx->launches++;
     return BIOIK_OK;
+}
+
+__global__ void k_broadcast(const double* __restrict__ src, int per, int B, double* __restrict__ dst)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < (size_t)B * per) dst[i] = src[i % per];
 }
 
 // view of queries [q0, q0 + nq) of a batch state
@@ -277,7 +317,9 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     {
         // no per-query parameters: broadcast the defaults of BioikGoal::p
         if((rc = ensure_staging(ctx, B)) != BIOIK_OK) return rc;
-        for(int b = 0; b < B; b++) CU(ctx, cudaMemcpyAsync(ctx->d_gp + (size_t)b * P.G * GOAL_NPARAM, ctx->d_default_gp, (size_t)P.G * GOAL_NPARAM * 8, cudaMemcpyDeviceToDevice, st));
+        const int per = P.G * GOAL_NPARAM;
+        k_broadcast<<<(int)(((size_t)B * per + 255) / 256), 256, 0, st>>>(ctx->d_default_gp, per, B, ctx->d_gp);
+        if((rc = check_launch(ctx, "k_broadcast")) != BIOIK_OK) return rc;
         d_gp = ctx->d_gp;
     }
     S.goal_params = d_gp;
@@ -332,27 +374,23 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         }
         auto launch_serial = [&](int h, int step, int phases) -> int {
             const int sgrid = (2 * Sh[h].B + pl.block - 1) / pl.block;
-            EventPair sp = get_pair(ctx, 1);
-            cudaEventRecord(sp.a, ss);
+            Timed tm(ctx, ss, 1);
             ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, phases);
             int r = check_launch(ctx, "k_serial");
-            cudaEventRecord(sp.b, ss);
-            ctx->pending.push_back(sp);
+            tm.done();
             if(H == 2) cudaEventRecord(ctx->ev_serial[h], ss);
             return r;
         };
         auto launch_evolve = [&](int h, int step) -> int {
             const int eb = (2 * Sh[h].B + warps_per_block - 1) / warps_per_block;
             if(H == 2) cudaStreamWaitEvent(se, ctx->ev_serial[h], 0);
-            EventPair ev = get_pair(ctx, 0);
-            cudaEventRecord(ev.a, se);
+            Timed tm(ctx, se, 0);
             if(fast)
                 fast<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step, ctx->d_mtab);
             else
                 k_evolve<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step);
             int r = check_launch(ctx, "k_evolve");
-            cudaEventRecord(ev.b, se);
-            ctx->pending.push_back(ev);
+            tm.done();
             if(H == 2) cudaEventRecord(ctx->ev_evolve[h], se);
             return r;
         };
@@ -379,23 +417,15 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     else
     for(int step = 0; step < steps; step++)
     {
-        EventPair s1 = get_pair(ctx, 1);
-        cudaEventRecord(s1.a, st);
+        Timed t1(ctx, st, 1);
         k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S);
         if((rc = check_launch(ctx, "k_prepare")) != BIOIK_OK) return rc;
-        cudaEventRecord(s1.b, st);
-        ctx->pending.push_back(s1);
-        EventPair ev = get_pair(ctx, 0);
-        cudaEventRecord(ev.a, st);
-        if(fast)
-            fast<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step, ctx->d_mtab);
-        else
-            k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
+        t1.done();
+        Timed t2(ctx, st, 0);
+        k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
         if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
-        cudaEventRecord(ev.b, st);
-        ctx->pending.push_back(ev);
-        EventPair s2 = get_pair(ctx, 1);
-        cudaEventRecord(s2.a, st);
+        t2.done();
+        Timed t3(ctx, st, 1);
         if(S.memetic)
         {
             k_memetic<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
@@ -403,8 +433,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         }
         k_species<<<qblocks, TPB, 0, st>>>(ctx->dP, S, step);
         if((rc = check_launch(ctx, "k_species")) != BIOIK_OK) return rc;
-        cudaEventRecord(s2.b, st);
-        ctx->pending.push_back(s2);
+        t3.done();
     }
     k_finalize<<<qblocks, TPB, 0, st>>>(ctx->dP, S, d_osol, d_ofit, d_osucc, d_osteps);
     if((rc = check_launch(ctx, "k_finalize")) != BIOIK_OK) return rc;
@@ -489,6 +518,8 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     {
         const char* fg = getenv("BIOIK_FORCE_GENERIC");
         ctx->force_generic = fg && fg[0] == '1';
+        const char* ng = getenv("BIOIK_NO_GRAPH");
+        ctx->use_graphs = !(ng && ng[0] == '1');
         const char* ch = getenv("BIOIK_EVOLVE_CH");
         if(ch && atoi(ch) > 0) ctx->ch_cap = atoi(ch);
         const char* np = getenv("BIOIK_PIPELINE"); // measured slower than the plain sequence on B200 (wave quantisation of the half grids): opt-in
@@ -503,6 +534,7 @@ void bioik_destroy(bioik_ctx* ctx)
     if(!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
+    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     for(auto& p : ctx->pending) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
@@ -542,6 +574,8 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     ctx->d_osucc = ctx->d_osteps = nullptr;
     ctx->stageB = 0;
     ctx->sched_steps = -1;
+    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+    ctx->graph_B = -1;
     ctx->has_problem = true;
     return BIOIK_OK;
 }
@@ -569,14 +603,52 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     if(goal_params) CU(ctx, cudaMemcpyAsync(ctx->d_gp, goal_params, (size_t)B * P.G * GOAL_NPARAM * 8, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->d_seeds, seeds, (size_t)B * P.n_vars * 8, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ctx->d_rs, rng_seeds, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
-    if(rc != BIOIK_OK) return rc;
+    // Repeated solves of one shape replay a CUDA graph of the ~50 kernel launches (first call eager: it sizes the
+    // state; second call captures; later calls replay).  Per-launch timing and graphs exclude each other.
+    const int has_gp = goal_params ? 1 : 0;
+    const bool same_shape = ctx->graph_B == B && ctx->graph_steps == steps && ctx->graph_early == early_exit && ctx->graph_gp == has_gp;
+    if(ctx->use_graphs && !ctx->timing && same_shape && ctx->graph_exec)
+    {
+        CU(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+        ctx->launches += ctx->graph_launches;
+    }
+    else if(ctx->use_graphs && !ctx->timing && same_shape)
+    {
+        cudaGraph_t graph = nullptr;
+        CU(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        ctx->capturing = true;
+        const int64_t l0 = ctx->launches;
+        rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+        ctx->capturing = false;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if(rc != BIOIK_OK)
+        {
+            if(graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if(ce != cudaSuccess) return fail(ctx, BIOIK_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        ctx->graph_launches = ctx->launches - l0;
+        ce = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if(ce != cudaSuccess)
+        {
+            ctx->graph_exec = nullptr;
+            return fail(ctx, BIOIK_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        }
+        CU(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+    }
+    else
+    {
+        if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+        rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+        if(rc != BIOIK_OK) return rc;
+        ctx->graph_B = B, ctx->graph_steps = steps, ctx->graph_early = early_exit, ctx->graph_gp = has_gp;
+    }
     if(out_solutions) CU(ctx, cudaMemcpyAsync(out_solutions, ctx->d_osol, (size_t)B * P.n_vars * 8, cudaMemcpyDeviceToHost, st));
     if(out_fitness) CU(ctx, cudaMemcpyAsync(out_fitness, ctx->d_ofit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if(out_success) CU(ctx, cudaMemcpyAsync(out_success, ctx->d_osucc, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_osteps, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
-    drain_events(ctx);
     return BIOIK_OK;
 }
 
@@ -694,8 +766,9 @@ int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int6
 {
     if(!ctx) return BIOIK_E_INVALID;
     CU(ctx, cudaSetDevice(ctx->cfg.device));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaDeviceSynchronize());
     drain_events(ctx);
+    ctx->timing = (reset != 2); // the first call switches per-launch timing on; reset == 2 switches it off again
     if(out_ms_evolve) *out_ms_evolve = ctx->ms_evolve;
     if(out_launches_evolve) *out_launches_evolve = ctx->n_evolve;
     if(out_ms_serial) *out_ms_serial = ctx->ms_serial;

@@ -120,11 +120,13 @@ class IKSolver:
     def launch_count(self):
         return int(self.lib.bioik_launch_count(self._ctx))
 
-    def kernel_time(self, reset=True):
-        """(ms in the generation kernel, its launches, ms in the serial kernels, their launches) since the last reset."""
+    def kernel_time(self, reset=True, disable=False):
+        """(ms in the generation kernel, its launches, ms in the serial kernels, their launches) since the last reset.
+        Per-launch CUDA-event timing is switched ON by the first call (it costs host time per launch and excludes
+        CUDA-graph replay) and OFF again with disable=True."""
         a, b = C.c_double(), C.c_double()
         na, nb = C.c_int64(), C.c_int64()
-        self._check(self.lib.bioik_kernel_time(self._ctx, int(reset), C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        self._check(self.lib.bioik_kernel_time(self._ctx, 2 if disable else int(reset), C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return a.value, na.value, b.value, nb.value
 
 

@@ -143,7 +143,8 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem);
  * replaced by a step budget (SURVEY.md §8(c) batch contract):
  *   query q starts as a freshly constructed solver sharing the lookup tables,
  *   rng = minstd_rand(rng_seeds[q]), runs `steps` step()s; success is tested on
- *   getSolution() after steps 1,5,9,... and after the last step; with
+ *   getSolution() after every 4th step (the driver's 4-step bursts,
+ *   src/ik_parallel.h:165-181) and after the last step; with
  *   early_exit != 0 a query stops at its first successful test, like the
  *   reference driver.
  * Host pointers; H2D/D2H copies are part of the call.
@@ -202,9 +203,12 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 int64_t bioik_launch_count(const bioik_ctx* ctx);
 
-/* Device-time of the dominant (generation) kernel accumulated since the last call
- * with reset != 0, measured with CUDA events on the launching stream; returns
- * milliseconds and the number of launches through the out parameters. */
+/* Device-time of the dominant (generation) kernel and of the serial kernels accumulated
+ * since the last call with reset != 0, measured with CUDA events on the launching
+ * stream; returns milliseconds and the number of launches through the out parameters.
+ * Per-launch timing is switched on by the first call (reset 0 or 1) and off again by
+ * reset == 2; while it is off, repeated bioik_solve_batch calls of one shape replay a
+ * CUDA graph. */
 int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int64_t* out_launches_evolve,
                       double* out_ms_serial, int64_t* out_launches_serial);
 

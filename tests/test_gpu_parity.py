@@ -224,12 +224,19 @@ def test_device_pointer_entry_point(oracle):
     succ = torch.empty(128, dtype=torch.int32, device=dev)
     stp = torch.empty(128, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream()
+    solver.kernel_time()  # switches per-launch timing on
     solver.solve_batch_device(128, gp.data_ptr(), seeds.data_ptr(), rs.data_ptr(), 6, False, sol.data_ptr(), fit.data_ptr(), succ.data_ptr(), stp.data_ptr(), stream=st.cuda_stream)
     st.synchronize()
     ref = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)
     assert np.array_equal(sol.cpu().numpy(), ref["solutions"]) and np.array_equal(fit.cpu().numpy(), ref["fitness"])
-    ev, nev, se, nse = solver.kernel_time()
-    assert nev >= 12 and ev > 0 and solver.launch_count() > 0
+    ev, nev, se, nse = solver.kernel_time(disable=True)
+    assert nev >= 6 and ev > 0 and solver.launch_count() > 0
+    # with timing off, repeated host-API solves of one shape replay a CUDA graph: same answers
+    for _ in range(3):
+        again = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)
+        assert np.array_equal(again["solutions"], ref["solutions"]) and np.array_equal(again["fitness"], ref["fitness"])
+    other = solver.solve_batch(w.goal_params[:50], w.seeds[:50], w.rng_seeds[:50], 6)  # shape change drops the graph
+    assert np.array_equal(other["solutions"], ref["solutions"][:50])
 
 
 def test_generic_and_fast_generation_kernels_agree(oracle, monkeypatch):
