@@ -20,7 +20,7 @@ JOINT_VARS = {JOINT_FIXED: 0, JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_FLOAT
 # goal types (include/bio_ik/goal_types.h)
 (GOAL_POSITION, GOAL_ORIENTATION, GOAL_POSE, GOAL_LOOK_AT, GOAL_MAX_DISTANCE, GOAL_MIN_DISTANCE, GOAL_LINE,
  GOAL_PLANE, GOAL_AVOID_JOINT_LIMITS, GOAL_CENTER_JOINTS, GOAL_REGULARIZATION, GOAL_MINIMAL_DISPLACEMENT,
- GOAL_JOINT_VARIABLE, GOAL_SIDE, GOAL_DIRECTION) = range(1, 16)
+ GOAL_JOINT_VARIABLE, GOAL_SIDE, GOAL_DIRECTION, GOAL_CONE) = range(1, 17)
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

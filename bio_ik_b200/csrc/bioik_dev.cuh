@@ -28,6 +28,15 @@
 #define BIOIK_FMAX(a, b) std::fmax((a), (b))
 #define BIOIK_ATAN2(a, b) std::atan2((a), (b))
 #define BIOIK_ACOS(a) std::acos(a)
+static inline double bioik_clear_low_word(double s)
+{
+    uint64_t b;
+    __builtin_memcpy(&b, &s, 8);
+    b &= 0xFFFFFFFF00000000ull;
+    __builtin_memcpy(&s, &b, 8);
+    return s;
+}
+#define BIOIK_CLEAR_LOW_WORD(s) bioik_clear_low_word(s)
 #else
 #define BIOIK_HD __device__ __forceinline__
 #define BIOIK_FMA(a, b, c) __fma_rn((a), (b), (c))
@@ -39,6 +48,7 @@
 #define BIOIK_FMAX(a, b) fmax((a), (b))
 #define BIOIK_ATAN2(a, b) atan2((a), (b))
 #define BIOIK_ACOS(a) acos(a)
+#define BIOIK_CLEAR_LOW_WORD(s) __hiloint2double(__double2hiint(s), 0)
 #endif
 
 namespace bioik
@@ -56,7 +66,7 @@ constexpr double DBLMAX = 1.7976931348623157e308;
 enum JointType { J_FIXED = 0, J_REVOLUTE = 1, J_PRISMATIC = 2, J_FLOATING = 3, J_PLANAR = 4 };
 enum GoalType {
     G_POSITION = 1, G_ORIENTATION, G_POSE, G_LOOK_AT, G_MAX_DISTANCE, G_MIN_DISTANCE, G_LINE, G_PLANE, G_AVOID_JOINT_LIMITS,
-    G_CENTER_JOINTS, G_REGULARIZATION, G_MINIMAL_DISPLACEMENT, G_JOINT_VARIABLE, G_SIDE, G_DIRECTION
+    G_CENTER_JOINTS, G_REGULARIZATION, G_MINIMAL_DISPLACEMENT, G_JOINT_VARIABLE, G_SIDE, G_DIRECTION, G_CONE
 };
 
 // ---------------------------------------------------------------------------
@@ -220,6 +230,68 @@ BIOIK_HD void d_sincos(double x, double& s_out, double& c_out)
     if((q + 1) & 2) c = -c;
     s_out = s;
     c_out = c;
+}
+
+// d_acos: arithmetic-contract acos of ConeGoal (fdlibm e_acos.c algorithm, IEEE operations only): identical
+// operation sequence in the CPU oracle (det_acos).
+BIOIK_HD double d_acos(double x)
+{
+    const double one = 1.0, pi = 3.14159265358979311600e+00, pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04,
+                 pS5 = 3.47933107596021167570e-05;
+    const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    const double ax = BIOIK_FABS(x);
+    if(!(ax < 1.0))
+    {
+        if(x == 1.0) return 0.0;
+        if(x == -1.0) return pi + 2.0 * pio2_lo;
+        return (x - x) / (x - x);
+    }
+    if(ax < 0.5)
+    {
+        if(ax < 6.938893903907228e-18) return pio2_hi + pio2_lo;
+        double z = x * x;
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        double r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if(x < 0)
+    {
+        double z = (one + x) * 0.5;
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        double s = BIOIK_SQRT(z);
+        double r = p / q;
+        double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    double z = (one - x) * 0.5;
+    double s = BIOIK_SQRT(z);
+    double df = BIOIK_CLEAR_LOW_WORD(s);
+    double c = (z - df * df) / (s + df);
+    double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    double r = p / q;
+    double w = r * s + c;
+    return 2.0 * (df + w);
+}
+
+// goal_types.h:700-711 on a frame f (px py pz qx qy qz qw)
+template <class AP, class AF> BIOIK_HD double cone_goal_value(AP p, AF f)
+{
+    double sum = 0.0;
+    V3 v = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[4], p[5], p[6]});
+    double s = BIOIK_SQRT((v.x * v.x + v.y * v.y + v.z * v.z) * (p[7] * p[7] + p[8] * p[8] + p[9] * p[9]));
+    double c = (v.x * p[7] + v.y * p[8] + v.z * p[9]) / s;
+    if(c < -1.0) c = -1.0;
+    if(c > 1.0) c = 1.0;
+    double d = BIOIK_FMAX(0.0, d_acos(c) - p[10]);
+    sum += d * d;
+    double w = p[3];
+    double dx = p[0] - f[0], dy = p[1] - f[1], dz = p[2] - f[2];
+    sum += w * w * (dx * dx + dy * dy + dz * dz);
+    return sum;
 }
 
 // src/utils.h:319
@@ -512,6 +584,7 @@ template <class AP, class AT, class AX, class AS> BIOIK_HD double goal_value(con
         V3 v = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[0], p[1], p[2]});
         return len2(p[3] - v.x, p[4] - v.y, p[5] - v.z);
     }
+    case G_CONE: return cone_goal_value(p, f);
     default: return 0.0;
     }
 }

@@ -151,6 +151,7 @@ BIOIK_HD double link_goal_value(int type, const double* p, const double* f)
         V3 v = quat_mul_vec(Q4{f[3], f[4], f[5], f[6]}, V3{p[0], p[1], p[2]});
         return len2(p[3] - v.x, p[4] - v.y, p[5] - v.z);
     }
+    case G_CONE: return cone_goal_value(p, f);
     default: return 0.0;
     }
 }

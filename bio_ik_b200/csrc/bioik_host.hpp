@@ -246,7 +246,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
     for(int g = 0; g < p->n_goals; g++)
     {
         const BioikGoal& bg = p->goals[g];
-        if(bg.type < BIOIK_GOAL_POSITION || bg.type > BIOIK_GOAL_DIRECTION) return host_fail(err, BIOIK_E_UNSUPPORTED_GOAL, "goal type has no device implementation (callback / FCL goals stay on the CPU solver)");
+        if(bg.type < BIOIK_GOAL_POSITION || bg.type > BIOIK_GOAL_CONE) return host_fail(err, BIOIK_E_UNSUPPORTED_GOAL, "goal type has no device implementation (callback / FCL goals stay on the CPU solver)");
         DGoal& D = P.goals[g];
         D.type = bg.type;
         D.tip = bg.tip;

@@ -278,6 +278,37 @@ class DirectionGoal(SideGoal):
     type = _abi.GOAL_DIRECTION
 
 
+class ConeGoal(LinkGoalBase):
+    """goal_types.h:646-712.  The three reference constructors: (link, axis, direction, angle, weight),
+    (link, position, axis, direction, angle, weight) -> position_weight 1, and
+    (link, position, position_weight, axis, direction, angle, weight)."""
+    type = _abi.GOAL_CONE
+
+    def __init__(self, link_name="", axis=(0, 0, 1), direction=(0, 0, 1), angle=0.0, weight=1.0, position=None, position_weight=None):
+        super().__init__(link_name, weight)
+        self.axis, self.direction, self.angle = _v3(axis), _v3(direction), float(angle)  # constructors do not normalise
+        self.position = _v3(position) if position is not None else (0.0, 0.0, 0.0)
+        self.position_weight = float(position_weight) if position_weight is not None else (1.0 if position is not None else 0.0)
+
+    def setAxis(self, a):
+        self.axis = _normalized3(a)
+
+    def setDirection(self, d):
+        self.direction = _normalized3(d)
+
+    def setAngle(self, a):
+        self.angle = float(a)
+
+    def setPosition(self, p):
+        self.position = _v3(p)
+
+    def setPositionWeight(self, w):
+        self.position_weight = float(w)
+
+    def params(self):
+        return _pad(list(self.position) + [self.position_weight] + list(self.axis) + list(self.direction) + [self.angle])
+
+
 class _HostOnlyGoal(Goal):
     def __init__(self, *a, **k):
         raise UnsupportedGoal(f"{type(self).__name__} needs a host callback / FCL and cannot run on the device "

@@ -276,6 +276,31 @@ public:
     int type() const override { return BIOIK_GOAL_DIRECTION; }
 };
 
+class ConeGoal : public LinkGoalBase // goal_types.h:646-712 (the three reference constructors)
+{
+    Vector3 position, axis{0, 0, 1}, direction{0, 0, 1};
+    double position_weight = 0, angle = 0;
+
+public:
+    ConeGoal() {}
+    ConeGoal(const std::string& link_name, const Vector3& axis, const Vector3& direction, double angle, double weight = 1.0) : LinkGoalBase(link_name, weight), axis(axis), direction(direction), angle(angle) {}
+    ConeGoal(const std::string& link_name, const Vector3& position, const Vector3& axis, const Vector3& direction, double angle, double weight = 1.0)
+        : LinkGoalBase(link_name, weight), position(position), axis(axis), direction(direction), position_weight(1), angle(angle)
+    {
+    }
+    ConeGoal(const std::string& link_name, const Vector3& position, double position_weight, const Vector3& axis, const Vector3& direction, double angle, double weight = 1.0)
+        : LinkGoalBase(link_name, weight), position(position), axis(axis), direction(direction), position_weight(position_weight), angle(angle)
+    {
+    }
+    void setPosition(const Vector3& p) { position = p; }
+    void setPositionWeight(double w) { position_weight = w; }
+    void setAxis(const Vector3& a) { axis = a.normalized(); }
+    void setDirection(const Vector3& d) { direction = d.normalized(); }
+    void setAngle(double a) { angle = a; }
+    int type() const override { return BIOIK_GOAL_CONE; }
+    void params(double* p) const override { BIOIK_V3(p, 0, position), p[3] = position_weight, BIOIK_V3(p, 4, axis), BIOIK_V3(p, 7, direction), p[10] = angle; }
+};
+
 #define BIOIK_JOINT_SPACE_GOAL(NAME, TYPE, SECONDARY_DEFAULT)                                    \
     class NAME : public Goal                                                                      \
     {                                                                                             \

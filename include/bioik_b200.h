@@ -64,7 +64,9 @@ enum {
     BIOIK_GOAL_MINIMAL_DISPLACEMENT = 12,/* goal_types.h:455-465 (no params)                            */
     BIOIK_GOAL_JOINT_VARIABLE = 13,      /* goal_types.h:494-498 var=robot variable, p[0]=position      */
     BIOIK_GOAL_SIDE = 14,                /* goal_types.h:606-613 p[0..2]=axis p[3..5]=direction         */
-    BIOIK_GOAL_DIRECTION = 15            /* goal_types.h:637-643 p[0..2]=axis p[3..5]=direction         */
+    BIOIK_GOAL_DIRECTION = 15,           /* goal_types.h:637-643 p[0..2]=axis p[3..5]=direction         */
+    BIOIK_GOAL_CONE = 16                 /* goal_types.h:700-711 p[0..2]=position p[3]=position_weight
+                                                                 p[4..6]=axis p[7..9]=direction p[10]=angle */
 };
 
 #define BIOIK_GOAL_NPARAM 12

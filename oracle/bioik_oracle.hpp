@@ -221,6 +221,55 @@ inline void det_sincos(double x, double* s_out, double* c_out)
     *c_out = c;
 }
 
+// det_acos: the arithmetic-contract acos for ConeGoal (tf2::Vector3::angle -> tf2Acos -> acos): the fdlibm
+// e_acos.c algorithm (rational approximation + sqrt), plain IEEE operations only, so CPU and GPU agree bit-for-bit.
+inline double det_acos(double x)
+{
+    const double one = 1.0, pi = 3.14159265358979311600e+00, pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04,
+                 pS5 = 3.47933107596021167570e-05;
+    const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    const double ax = std::fabs(x);
+    if(!(ax < 1.0))
+    {
+        if(x == 1.0) return 0.0;
+        if(x == -1.0) return pi + 2.0 * pio2_lo;
+        return (x - x) / (x - x); // NaN
+    }
+    if(ax < 0.5)
+    {
+        if(ax < 6.938893903907228e-18) return pio2_hi + pio2_lo; // 2^-57
+        double z = x * x;
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        double r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if(x < 0)
+    {
+        double z = (one + x) * 0.5;
+        double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        double s = std::sqrt(z);
+        double r = p / q;
+        double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    double z = (one - x) * 0.5;
+    double s = std::sqrt(z);
+    uint64_t bits;
+    std::memcpy(&bits, &s, 8);
+    bits &= 0xFFFFFFFF00000000ull; // df = s with the low word cleared
+    double df;
+    std::memcpy(&df, &bits, 8);
+    double c = (z - df * df) / (s + df);
+    double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    double q = one + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    double r = p / q;
+    double w = r * s + c;
+    return 2.0 * (df + w);
+}
+
 struct Options
 {
     bool libm_sincos = false; // use libm sin/cos instead of det_sincos (deviation study only)
@@ -735,7 +784,8 @@ enum GoalKind
     G_MINIMAL_DISPLACEMENT = 12,
     G_JOINT_VARIABLE = 13,
     G_SIDE = 14,
-    G_DIRECTION = 15
+    G_DIRECTION = 15,
+    G_CONE = 16
 };
 static const int GOAL_NPARAM = 12;
 
@@ -901,6 +951,23 @@ struct Problem
             Vec3 v;
             quat_mul_vec(tip_frames[g.tip_index].rot, Vec3(p[0], p[1], p[2]), v);
             return distance2(v, Vec3(p[3], p[4], p[5]));
+        }
+        case G_CONE: // goal_types.h:700-711; tf2::Vector3::angle(v) = tf2Acos(dot(v) / sqrt(length2() * v.length2())), tf2Acos clamps to [-1, 1]
+        {
+            double sum = 0.0;
+            const Frame& fb = tip_frames[g.tip_index];
+            Vec3 v;
+            quat_mul_vec(fb.rot, Vec3(p[4], p[5], p[6]), v);
+            Vec3 direction(p[7], p[8], p[9]);
+            double s = std::sqrt(length2(v) * length2(direction));
+            double c = dot(v, direction) / s;
+            if(c < -1.0) c = -1.0;
+            if(c > 1.0) c = 1.0;
+            double d = std::fmax(0.0, det_acos(c) - p[10]);
+            sum += d * d;
+            double w = p[3];
+            sum += w * w * length2(Vec3(p[0], p[1], p[2]) - fb.pos);
+            return sum;
         }
         default: throw std::runtime_error("oracle: unsupported goal type");
         }

@@ -155,6 +155,10 @@ void oracle_minstd_index(uint32_t seed, uint64_t s, int n, uint64_t* out)
     std::minstd_rand rng(seed);
     for(int i = 0; i < n; i++) out[i] = std::uniform_int_distribution<size_t>(0, s - 1)(rng);
 }
+void oracle_acos(int n, const double* x, double* out)
+{
+    for(int i = 0; i < n; i++) out[i] = det_acos(x[i]);
+}
 void oracle_sincos(int n, const double* x, double* s, double* c)
 {
     for(int i = 0; i < n; i++) det_sincos(x[i], s + i, c + i);

@@ -35,6 +35,7 @@ class Oracle:
         lib.oracle_minstd_normal.argtypes = [C.c_uint32, C.c_int, dp]
         lib.oracle_minstd_index.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
         lib.oracle_sincos.argtypes = [C.c_int, dp, dp, dp]
+        lib.oracle_acos.argtypes = [C.c_int, dp, dp]
         lib.oracle_concat.argtypes = [dp, dp, dp]
         lib.oracle_invert.argtypes = [dp, dp]
         lib.oracle_change.argtypes = [dp, dp, dp, dp]
@@ -67,6 +68,12 @@ class Oracle:
         s, c = np.empty_like(x), np.empty_like(x)
         self.lib.oracle_sincos(len(x), _abi.dptr(x), _abi.dptr(s), _abi.dptr(c))
         return s, c
+
+    def acos(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self.lib.oracle_acos(len(x), _abi.dptr(x), _abi.dptr(out))
+        return out
 
     def fk(self, robot, problem, variables, libm=False, links=False):
         v = np.ascontiguousarray(variables, dtype=np.float64).reshape(-1, robot.n_vars)

@@ -91,7 +91,8 @@ def test_mixed_goals_fast_kernel(sim, oracle):
     g = groups["all"]
     r, l = "r_wrist_roll_link", "l_wrist_roll_link"
     gl = [G.PositionGoal(r, (0.6, -0.3, 0.9)), G.LookAtGoal(l, (1, 0, 0), (2, 0.5, 1), 0.3), G.JointVariableGoal("torso_lift_joint", 0.2, 2.0), G.CenterJointsGoal(0.5, secondary=False),
-          G.LineGoal(l, (0.5, 0.2, 1), (1, 1, 0), 0.7), G.MinimalDisplacementGoal(1.5), G.AvoidJointLimitsGoal(0.8), G.DirectionGoal(r, (1, 0, 0), (0, 0, 1), 0.4)]
+          G.LineGoal(l, (0.5, 0.2, 1), (1, 1, 0), 0.7), G.MinimalDisplacementGoal(1.5), G.AvoidJointLimitsGoal(0.8), G.DirectionGoal(r, (1, 0, 0), (0, 0, 1), 0.4),
+          G.ConeGoal(l, (1, 0, 0), (0, 0.6, 0.8), 0.4, weight=0.3)]
     pr = Problem().initialize(rm, g, gl)
     rng = np.random.default_rng(5)
     seeds = workloads.sample_configurations(rm, pr.active_variables, 3, rng)

@@ -105,6 +105,17 @@ def test_det_sincos_accuracy(oracle):
     assert np.all(np.isnan(s)) and np.all(np.isnan(c))
 
 
+def test_det_acos_accuracy(oracle):
+    """det_acos (ConeGoal's arithmetic-contract acos, fdlibm algorithm) is within 1 ulp of libm."""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-1, 1, 200000), np.linspace(-1, 1, 20001), [0.0, 0.5, -0.5, 1.0, -1.0, 1e-20, 0.4999999999, 0.5000000001]])
+    a = oracle.acos(x)
+    ref = np.arccos(x)
+    err = np.abs(a - ref) / np.spacing(np.maximum(ref, 1e-300))
+    assert err.max() <= 1.0
+    assert oracle.acos(np.array([1.0]))[0] == 0.0 and np.isnan(oracle.acos(np.array([1.5]))[0])
+
+
 def numpy_fk(robot, variables):
     """Independent exact FK (scipy rotations), returns link frames [L][7]."""
     a = robot.arrays
@@ -210,7 +221,8 @@ def test_approx_fitness_matches_formula(oracle):
     rm, groups = robots.pr2_like()
     g = groups["right_arm"]
     goal = G.PoseGoal("r_wrist_roll_link", (0.6, -0.2, 0.9), (0, 0, 0.3, 1.0))
-    pr = Problem().initialize(rm, g, [goal, G.MinimalDisplacementGoal(2.0)])
+    cone = G.ConeGoal("r_wrist_roll_link", (1, 0, 0), (0, 0.6, 0.8), 0.3, weight=0.5, position=(0.5, 0, 1), position_weight=0.7)
+    pr = Problem().initialize(rm, g, [goal, G.MinimalDisplacementGoal(2.0), cone])
     rng = np.random.default_rng(11)
     base = workloads.sample_configurations(rm, pr.active_variables, 3, rng)
     n = len(pr.active_variables)
@@ -226,7 +238,13 @@ def test_approx_fitness_matches_formula(oracle):
             d = genes[b, m] - base[b, pr.active_variables]
             f = tip0[b, 0] + d @ delta[b, 0]
             e = ((f[:3] - p[:3]) ** 2).sum() + min(((p[3:7] - f[3:]) ** 2).sum(), ((p[3:7] + f[3:]) ** 2).sum()) * 0.25
-            assert math.isclose(prim[b, m], e, rel_tol=1e-12)
+            # ConeGoal: quat_mul_vec(q, axis) by its defining formula r = v + 2 (q_w t + q_xyz x t), t = q_xyz x v (q is NOT normalised here)
+            qv, qw, ax = f[3:6], f[6], np.array([1.0, 0, 0])
+            t = np.cross(qv, ax)
+            v = ax + 2 * (qw * t + np.cross(qv, t))
+            ang = math.acos(max(-1.0, min(1.0, float(np.dot(v, [0, 0.6, 0.8]) / math.sqrt((v @ v) * 1.0)))))
+            ec = max(0.0, ang - 0.3) ** 2 + 0.49 * ((np.array([0.5, 0, 1]) - f[:3]) ** 2).sum()
+            assert math.isclose(prim[b, m], e + 0.25 * ec, rel_tol=1e-11)
             assert math.isclose(sec[b, m], 4.0 * ((d * vw) ** 2).sum(), rel_tol=1e-12)
 
 
