@@ -59,7 +59,7 @@ constexpr int MAX_VARS = 64;   // robot variables
 constexpr int MAX_GENES = 48;  // active variables
 constexpr int MAX_SLOTS = 96;  // links in the FK schedule
 constexpr int MAX_TIPS = 8;
-constexpr int MAX_GOALS = 16;
+constexpr int MAX_GOALS = 24;
 constexpr int GOAL_NPARAM = 12;
 constexpr double DBLMAX = 1.7976931348623157e308;
 

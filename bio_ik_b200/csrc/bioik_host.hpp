@@ -134,7 +134,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
     memset(&P, 0, sizeof(P));
     if(p->n_tips < 1 || p->n_active < 1 || p->n_goals < 1) return host_fail(err, BIOIK_E_INVALID, "problem needs at least one tip, one active variable and one goal");
     if(p->n_tips > MAX_TIPS || p->n_active > MAX_GENES || p->n_goals > MAX_GOALS || R.n_vars > MAX_VARS)
-        return host_fail(err, BIOIK_E_LIMIT, "problem exceeds compiled-in capacity (tips<=8, genes<=48, goals<=16, vars<=64)");
+        return host_fail(err, BIOIK_E_LIMIT, "problem exceeds compiled-in capacity (tips<=8, genes<=48, goals<=24, vars<=64)");
     P.n_vars = R.n_vars;
     P.n = p->n_active;
     P.T = p->n_tips;
