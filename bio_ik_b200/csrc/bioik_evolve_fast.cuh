@@ -375,6 +375,7 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
         // this lane's two best children so far: (key, packed = position * 512 + child)
         uint64_t k1 = FAST_KEY_NONE, k2 = FAST_KEY_NONE;
         uint32_t q1 = 0xFFFFFFFFu, q2 = 0xFFFFFFFFu;
+        double b1 = 0.0, b2 = 0.0; // fitness values of q1 / q2 while no pre-selection is active
 
         for(int chunk = 0; chunk < nchunks; chunk++)
         {
@@ -396,17 +397,16 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
             const double* dp = s_delta;
 
             // mutation terms are fetched one gene ahead of their use (L1/L2 latency off the dependent chain)
-            double mnext[CH];
+            // (two register buffers used alternately: no register rotation in the loop)
+            double mA[CH], mB[CH];
 #pragma unroll
-            for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
+            for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + 32 * k);
 
             // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
-            auto gene_step = [&](auto first_tag, int i) {
+            auto gene_step = [&](auto first_tag, int i, const double (&m)[CH], double (&mnext)[CH]) {
                 constexpr bool FIRST = decltype(first_tag)::value;
                 const double g0 = rp[0], base = rp[1], lo = rp[2], hi = rp[3];
-                double d[CH], x[CH], m[CH];
-#pragma unroll
-                for(int k = 0; k < CH; k++) m[k] = mnext[k];
+                double d[CH], x[CH];
                 mp += R;
                 if(i + 1 < n)
                 {
@@ -454,9 +454,17 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
                         }
                 }
             };
-            gene_step(std::true_type{}, 0);
+            gene_step(std::true_type{}, 0, mA, mB);
+            {
+                int i = 1;
 #pragma unroll 1
-            for(int i = 1; i < n; i++) gene_step(std::false_type{}, i);
+                for(; i + 1 < n; i += 2)
+                {
+                    gene_step(std::false_type{}, i, mB, mA);
+                    gene_step(std::false_type{}, i + 1, mA, mB);
+                }
+                if(i < n) gene_step(std::false_type{}, i, mB, mA);
+            }
 
             // fitness: weighted sum in goal order (src/problem.cpp:251-257)
 #pragma unroll
@@ -514,21 +522,27 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
                 }
                 else if(c < C)
                 {
-                    // running top-2 of this lane; position == child slot without pre-selection
-                    // a lane meets its children in increasing position order, so ties keep the earlier one: strict < only
-                    uint64_t kk = fast_fitness_key(prim);
-                    uint32_t pk = (uint32_t)c * 512u + (uint32_t)c;
-                    if(kk < k1)
+                    // running top-2 of this lane on the fitness VALUES; position == child slot without pre-selection.
+                    // Order = order of the integer keys: any number beats a NaN, and since a lane meets its children in
+                    // increasing position order ties keep the earlier one (strict <).
+                    const uint32_t pk = (uint32_t)c * 512u + (uint32_t)c;
+                    const bool ok = prim == prim;
+                    if(q1 == 0xFFFFFFFFu || prim < b1 || (b1 != b1 && ok))
                     {
-                        k2 = k1; q2 = q1;
-                        k1 = kk; q1 = pk;
+                        b2 = b1; q2 = q1;
+                        b1 = prim; q1 = pk;
                     }
-                    else if(kk < k2)
+                    else if(q2 == 0xFFFFFFFFu || prim < b2 || (b2 != b2 && ok))
                     {
-                        k2 = kk; q2 = pk;
+                        b2 = prim; q2 = pk;
                     }
                 }
             }
+        }
+        if(!P.has_secondary)
+        {
+            k1 = q1 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b1);
+            k2 = q2 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b2);
         }
 
         if(P.has_secondary)
