@@ -8,7 +8,9 @@ solves its own B-query shard; N>1 adds one NCCL all-gather of the result slab pe
   value      device-resident inputs, CUDA-event timed, max over ranks          (whole-job solves/s)
   e2e        the public host-buffer API (bioik_solve_batch): pinned host inputs, H2D + D2H inside
   roofline   generation kernel: algorithmic bytes / its CUDA-event time vs measured HBM peak
-  cpu_baseline / --impl reference   the CPU oracle port (reference flags, all host threads) on a bounded sample
+  cpu_baseline / --impl reference   the reference's own bio2_memetic code compiled with its Release flags
+             (oracle/_ref/libbioik_ref_fast.so, kind "reference"; child pool re-sized to pop=128 by the harness),
+             else the oracle port (kind "port"); all usable host threads, bounded sample of the same workload
 """
 import argparse
 import json
@@ -114,14 +116,28 @@ def usable_cpus():
     return n
 
 
-def cpu_port_rate(args, w_small, seconds, variant="fast"):
-    """Times the oracle port (same source, reference flags: oracle/Makefile) on all host threads over a
-    bounded sample of the workload.  Returns (solves/s, threads, sample description)."""
+def cpu_solver():
+    """(object with .solve(...), kind): the reference's own code built with its Release flags when oracle/_ref/ holds
+    it (built here from /root/reference by __graft_entry__.build(); the prebuilt .so travels to the GPU box), else the
+    oracle port built with the same flags."""
     import oracle_lib
-    o = oracle_lib.Oracle(variant)
+    if os.path.exists(oracle_lib.ref_lib_path("fast")) and not os.environ.get("BIOIK_BENCH_CPU_PORT"):
+        try:
+            return oracle_lib.Reference("fast"), "reference"
+        except OSError:
+            pass
+    o = oracle_lib.Oracle("fast")
+    o.tables(1)
+    return o, "port"
+
+
+def cpu_rate(args, w_small, seconds):
+    """Times the CPU implementation on all usable host threads over a bounded sample of the workload.
+    Returns (solves/s, threads, kind, sample description)."""
+    import oracle_lib
+    o, kind = cpu_solver()
     cfg = oracle_lib.make_cfg(population=args.population)
     threads = usable_cpus()
-    o.tables(cfg.table_seed)
     n0 = min(len(w_small.seeds), max(64, 4 * threads))
     t0 = time.perf_counter()
     o.solve(w_small.robot, w_small.problem, cfg, w_small.goal_params[:n0], w_small.seeds[:n0], w_small.rng_seeds[:n0], args.solver_steps, nthreads=threads)
@@ -132,13 +148,13 @@ def cpu_port_rate(args, w_small, seconds, variant="fast"):
     t0 = time.perf_counter()
     o.solve(w_small.robot, w_small.problem, cfg, gp, sd, rs, args.solver_steps, nthreads=threads)
     dt = time.perf_counter() - t0
-    return n1 / dt, threads, f"{n1} queries drawn from the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {threads} threads, {dt:.1f} s"
+    return n1 / dt, threads, kind, f"{n1} queries drawn from the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {threads} threads, {dt:.1f} s"
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference cannot be built
-    in this image (ROS/MoveIt/tf2/Eigen/KDL/FCL/Boost absent), so this is the oracle PORT built with the
-    reference's flags, all host threads, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores - its own
+    ik_evolution_2.cpp / problem.cpp / forward_kinematics.h compiled with its Release flags (oracle/_ref, see
+    oracle/Makefile) when present, else the oracle port; all usable threads, each step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,9 +164,8 @@ def run_reference(args):
     threads = usable_cpus()
     sample = int(min(args.batch, max(256, 256 * threads)))
     w.generate(lambda rm, pr, v: o.fk(rm, pr, v), B=sample, cfg_id=cid, seed_noise=(0.1 if args.config == "cfg4" else None))
-    fast = oracle_lib.Oracle("fast")
+    fast, kind = cpu_solver()
     cfg = oracle_lib.make_cfg(population=args.population)
-    fast.tables(cfg.table_seed)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -164,8 +179,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w.name, "batch_per_step": sample, "population": args.population, "solver_steps": args.solver_steps, "generations": 8 * args.solver_steps,
-                   "note": "CPU port of the reference path (reference not buildable offline); each step = bounded sample of the 10k batch"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"{sample} queries per step x {args.steps} steps", "host_hw_threads": os.cpu_count()},
+                   "note": ("the reference's own solver sources compiled with its Release flags (oracle/_ref)" if kind == "reference" else "CPU port of the reference path (oracle/_ref absent)")
+                           + "; each step = bounded sample of the batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} queries per step x {args.steps} steps", "host_hw_threads": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -324,8 +340,8 @@ def main():
         wcpu, _ = make_workload(args, None)
         nb = B
         wcpu.goal_params, wcpu.seeds, wcpu.rng_seeds = batches[0][0][:nb], batches[0][1][:nb], batches[0][2][:nb]
-        rate, threads, desc = cpu_port_rate(args, wcpu, args.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc, "host_hw_threads": os.cpu_count()}
+        rate, threads, kind, desc = cpu_rate(args, wcpu, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc, "host_hw_threads": os.cpu_count()}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

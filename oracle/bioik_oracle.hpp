@@ -6,13 +6,20 @@
 // --impl reference legs may build, load or call anything under oracle/.  The
 // product library (libbioik_b200.so) never links or calls this code.
 //
-// PARITY UNPINNED: the reference cannot be compiled in this image (needs ROS,
-// MoveIt, tf2, Eigen, KDL, FCL, Boost — SURVEY.md §8(c)) and its own tests pin
-// only the concat/invert/change algebra (test/utest.cpp:63-81, ported to
-// tests/test_oracle_math.py).  Everything else is validated by construction
-// (tests/test_oracle_*.py): exact FK vs an independent scipy implementation,
-// Jacobian vs central differences, approximator error O(d^2), RNG known-answer
-// values, FK->IK->FK round trips.
+// PARITY PINNED against the reference's own code.  The reference's build system cannot run in this image (catkin,
+// ROS, MoveIt, tf2, Eigen, KDL, FCL, Boost are absent), but the two translation units of this path
+// (src/ik_evolution_2.cpp, src/problem.cpp, with every bio_ik header they include) compile where they lie against
+// the stand-in third-party headers of oracle/shims/ (oracle/Makefile target `ref` -> oracle/_ref/).
+// tests/test_reference_pin.py compares this restatement with that build BIT FOR BIT - lookup tables, exact FK,
+// delta frames, approximated frames, every device goal class, Problem::initialize's ordering, and whole 25-step
+// solves (genes, gradients, species fitness, solutions, success) in all three bio2 modes, on all five BASELINE
+// configurations, at population 4..128, with mimic / prismatic joints and random trees.  Two switches are flipped
+// for that comparison, both documented deviations of the contract below: libm sin/cos (Options::libm_sincos) and
+// the stale-tip quirk Q2 (Options::stale_tips).  The reference's own unit tests pin only the concat / invert /
+// change algebra (test/utest.cpp:63-81, restated in tests/test_oracle.py).
+// What the pin does NOT cover: the shims restate third-party behaviour (tf2 LinearMath, KDL frames, Eigen's
+// matrix->quaternion), so a difference between a shim and the real library would go unnoticed; ConeGoal's acos is
+// compared to rounding only (det_acos vs libm).
 //
 // Arithmetic contract (shared with the CUDA kernels so results are bit-identical,
 // far inside the 1e-5 tolerance of BASELINE.json):
@@ -274,6 +281,9 @@ struct Options
 {
     bool libm_sincos = false; // use libm sin/cos instead of det_sincos (deviation study only)
     bool fma_approx = true;   // FMA in the approximator like the reference's AVX path; false = scalar path (:1174-1233)
+    bool fma_approx1 = true;  // same switch for computeApproximateMutation1 alone (experiments)
+    bool stale_tips = false;  // emulate quirk Q2 of the reference (forward_kinematics.h:940): tips a variable does not move keep
+                              // whatever the output buffer held before (pinning study only; never set on the parity path)
 };
 
 // ---------------------------------------------------------------------------
@@ -714,19 +724,20 @@ public:
         {
             if(mutation_approx_mask[itip][variable_index] == 0)
             {
-                output[itip] = input[itip]; // intended semantics, see header comment (reference leaves stale data)
+                if(!opt.stale_tips) output[itip] = input[itip]; // intended semantics, see header comment (reference leaves stale data)
                 continue;
             }
             const Frame& jd = mutation_approx_frames[itip][variable_index];
             const Frame& tf = input[itip];
             Frame o;
-            o.pos.x = madd(variable_delta, jd.pos.x, tf.pos.x);
-            o.pos.y = madd(variable_delta, jd.pos.y, tf.pos.y);
-            o.pos.z = madd(variable_delta, jd.pos.z, tf.pos.z);
-            o.rot.x = madd(variable_delta, jd.rot.x, tf.rot.x);
-            o.rot.y = madd(variable_delta, jd.rot.y, tf.rot.y);
-            o.rot.z = madd(variable_delta, jd.rot.z, tf.rot.z);
-            o.rot.w = madd(variable_delta, jd.rot.w, tf.rot.w);
+            auto madd1 = [&](double f, double d, double acc) { return opt.fma_approx1 ? madd(f, d, acc) : acc + d * f; };
+            o.pos.x = madd1(variable_delta, jd.pos.x, tf.pos.x);
+            o.pos.y = madd1(variable_delta, jd.pos.y, tf.pos.y);
+            o.pos.z = madd1(variable_delta, jd.pos.z, tf.pos.z);
+            o.rot.x = madd1(variable_delta, jd.rot.x, tf.rot.x);
+            o.rot.y = madd1(variable_delta, jd.rot.y, tf.rot.y);
+            o.rot.z = madd1(variable_delta, jd.rot.z, tf.rot.z);
+            o.rot.w = madd1(variable_delta, jd.rot.w, tf.rot.w);
             output[itip] = o;
         }
     }

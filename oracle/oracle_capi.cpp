@@ -218,6 +218,18 @@ int oracle_fk_batch(const BioikRobot* robot, const BioikProblem* problem, int li
     }
 }
 
+// deviation-study switch for the component entry points below: bit0 = libm sincos (what the reference calls)
+static int g_component_flags = 0;
+void oracle_set_component_flags(int flags) { g_component_flags = flags; }
+static Options componentOptions()
+{
+    Options opt;
+    opt.libm_sincos = (g_component_flags & 1) != 0;
+    opt.fma_approx = (g_component_flags & 2) == 0;
+    opt.fma_approx1 = (g_component_flags & 6) == 0;
+    return opt;
+}
+
 // delta frames [B][T][n_active][7]; mask [B][T][n_active] (may be NULL); jacobian [B][6T][n_active] (may be NULL)
 int oracle_approx_batch(const BioikRobot* robot, const BioikProblem* problem, int B, const double* variables, double* out_delta, int32_t* out_mask, double* out_jacobian)
 {
@@ -225,7 +237,7 @@ int oracle_approx_batch(const BioikRobot* robot, const BioikProblem* problem, in
     {
         RobotModel rm = makeRobot(robot);
         Problem pr = makeProblem(rm, problem);
-        RobotFK fk(&rm);
+        RobotFK fk(&rm, componentOptions());
         fk.initialize(pr.tip_link_indices);
         size_t T = pr.tip_link_indices.size(), n = pr.active_variables.size();
         for(int b = 0; b < B; b++)
@@ -260,7 +272,7 @@ int oracle_approx_fitness_batch(const BioikRobot* robot, const BioikProblem* pro
         RobotModel rm = makeRobot(robot);
         Problem pr0 = makeProblem(rm, problem);
         size_t n = pr0.active_variables.size();
-        RobotFK fk(&rm);
+        RobotFK fk(&rm, componentOptions());
         fk.initialize(pr0.tip_link_indices);
         std::vector<Frame> null_frames(pr0.tip_link_indices.size());
         for(int b = 0; b < B; b++)
@@ -289,8 +301,40 @@ int oracle_approx_fitness_batch(const BioikRobot* robot, const BioikProblem* pro
     }
 }
 
+// approximated tip frames [B][M][T][7] of genotypes [B][M][n] at base points [B][n_vars] (K2 alone)
+int oracle_approx_frames_batch(const BioikRobot* robot, const BioikProblem* problem, int B, int M, const double* base_variables, const double* genotypes, double* out_frames)
+{
+    try
+    {
+        RobotModel rm = makeRobot(robot);
+        Problem pr = makeProblem(rm, problem);
+        size_t n = pr.active_variables.size(), T = pr.tip_link_indices.size();
+        RobotFK fk(&rm, componentOptions());
+        fk.initialize(pr.tip_link_indices);
+        for(int b = 0; b < B; b++)
+        {
+            std::vector<double> v(base_variables + (size_t)b * rm.n_vars, base_variables + (size_t)(b + 1) * rm.n_vars);
+            fk.applyConfiguration(v);
+            fk.initializeMutationApproximator(pr.active_variables);
+            std::vector<const double*> gp(M);
+            for(int m = 0; m < M; m++) gp[m] = genotypes + ((size_t)b * M + m) * n;
+            std::vector<std::vector<Frame>> ph;
+            fk.computeApproximateMutations(M, gp.data(), ph);
+            for(int m = 0; m < M; m++)
+                for(size_t t = 0; t < T; t++) W7(ph[m][t], out_frames + (((size_t)b * M + m) * T + t) * 7);
+        }
+        return 0;
+    }
+    catch(std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 // ---- the batch solve (SURVEY.md §8(c) batch contract) ------------------------------------------
-// flags: bit0 = libm sincos, bit1 = scalar (non-FMA) approximator
+// flags: bit0 = libm sincos, bit1 = scalar (non-FMA) approximator, bit2 = scalar computeApproximateMutation1 only,
+//        bit3 = emulate the reference's stale-tip quirk Q2 (pinning study, test_reference_pin.py)
 // trace outputs (may be NULL): genes/gradients [B][2][2][n], species_fitness [B][2]
 int oracle_solve_batch(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, void* tables, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit,
                        int flags, int nthreads, double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_steps, double* out_genes, double* out_gradients, double* out_species_fitness)
@@ -304,6 +348,8 @@ int oracle_solve_batch(const BioikRobot* robot, const BioikProblem* problem, con
         Options opt;
         opt.libm_sincos = (flags & 1) != 0;
         opt.fma_approx = (flags & 2) == 0;
+        opt.fma_approx1 = (flags & 4) == 0;
+        opt.stale_tips = (flags & 8) != 0;
         size_t n = pr0.active_variables.size();
         std::atomic<int> failed(0);
         std::string err;

@@ -42,6 +42,8 @@ class Oracle:
         lib.oracle_fk_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp]
         lib.oracle_approx_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, dp, dp, ip, dp]
         lib.oracle_approx_fitness_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
+        lib.oracle_approx_frames_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp]
+        lib.oracle_set_component_flags.argtypes = [C.c_int]
         lib.oracle_solve_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_void_p, C.c_int, dp, dp, up,
                                            C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp]
         lib.oracle_hardware_threads.restype = C.c_int
@@ -106,6 +108,19 @@ class Oracle:
         self._check(self.lib.oracle_approx_fitness_batch(C.byref(r), C.byref(p), B, M, _abi.dptr(gp), _abi.dptr(seeds), _abi.dptr(base), _abi.dptr(g), _abi.dptr(prim), _abi.dptr(sec)))
         return prim, sec
 
+    def approx_frames(self, robot, problem, base, genotypes):
+        base = np.ascontiguousarray(base, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, n, T = base.shape[0], len(problem.active_variables), len(problem.tip_link_indices)
+        g = np.ascontiguousarray(genotypes, dtype=np.float64).reshape(B, -1, n)
+        out = np.zeros((B, g.shape[1], T, 7))
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.oracle_approx_frames_batch(C.byref(r), C.byref(p), B, g.shape[1], _abi.dptr(base), _abi.dptr(g), _abi.dptr(out)))
+        return out
+
+    def component_flags(self, flags):
+        """bit0: libm sin/cos (as the reference calls) in fk / approx / approx_fitness / approx_frames"""
+        self.lib.oracle_set_component_flags(int(flags))
+
     def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, flags=0, nthreads=0, table_seed=None):
         seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
         B, n = seeds.shape[0], len(problem.active_variables)
@@ -128,3 +143,103 @@ def make_cfg(population=18, generations=8, memetic="q", memetic_iters=8, table_s
     c.memetic = ord(memetic) if isinstance(memetic, str) and memetic else int(memetic or 0)
     c.memetic_iters, c.table_seed, c.device = memetic_iters, table_seed, device
     return c
+
+
+# ---------------------------------------------------------------------------------------------
+# the REFERENCE's own code (oracle/_ref/, built by `make -C oracle ref` where /root/reference exists)
+# ---------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+
+def ref_lib_path(variant="strict"):
+    return os.path.join(REF_DIR, f"libbioik_ref_{variant}.so")
+
+
+def build_ref():
+    """Compile the reference's bio2 solver sources in place (never copied); False when they are not on this machine."""
+    if not os.path.exists(os.path.join(REFERENCE_ROOT, "src", "ik_evolution_2.cpp")):
+        return os.path.exists(ref_lib_path("strict")) and os.path.exists(ref_lib_path("fast"))
+    return subprocess.run(["make", "-C", ORACLE_DIR, "-s", "ref"]).returncode == 0
+
+
+class Reference:
+    """ctypes front of oracle/ref_harness.cpp: same batch contract as Oracle.solve / approx_fitness, executed by
+    the reference's IKEvolution2 / RobotFK_Fast / Problem classes."""
+
+    def __init__(self, variant="strict"):
+        path = ref_lib_path(variant)
+        if not os.path.exists(path) and not build_ref():
+            raise FileNotFoundError(path)
+        self.lib = lib = C.CDLL(path)
+        dp, ip, up = _abi.c_double_p, _abi.c_int32_p, _abi.c_uint32_p
+        RP, PP = C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem)
+        lib.ref_last_error.restype = C.c_char_p
+        lib.ref_solve_batch.argtypes = [RP, PP, C.POINTER(_abi.BioikSolverCfg), C.c_void_p, C.c_int, dp, dp, up, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp]
+        lib.ref_approx_fitness_batch.argtypes = [RP, PP, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+        lib.ref_effective_goal_params.argtypes = [RP, PP, C.c_int, dp, dp]
+        lib.ref_effective_link_origins.argtypes = [RP, dp]
+        lib.ref_table.argtypes = [C.c_int, C.c_uint32]
+        lib.ref_table.restype = dp
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("reference: " + self.lib.ref_last_error().decode())
+
+    def _gp(self, problem, goal_params, B):
+        gp = np.repeat(problem.default_goal_params()[None], B, 0) if goal_params is None else goal_params
+        return np.ascontiguousarray(gp, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
+
+    def table(self, which, seed, n=1 << 23):
+        return np.ctypeslib.as_array(self.lib.ref_table(which, seed), shape=(1 << 23,))[:n].copy()
+
+    def effective_robot(self, robot):
+        """copy of `robot` whose link origins are the frames the reference derives from the same robot (its
+        Isometry3d -> quaternion conversion, forward_kinematics.h:203); differs from the input by at most an ulp"""
+        import copy
+        out = np.zeros((len(robot.links), 7))
+        r = robot.to_abi()
+        self._check(self.lib.ref_effective_link_origins(C.byref(r), _abi.dptr(out)))
+        src = robot.arrays["link_origin"].reshape(-1, 7)
+        sign = np.where((out[:, 3:] * src[:, 3:]).sum(axis=1) < 0, -1.0, 1.0)[:, None]  # q and -q are the same rotation
+        assert np.allclose(out[:, :3], src[:, :3], rtol=0, atol=0) and np.allclose(out[:, 3:] * sign, src[:, 3:], rtol=0, atol=1e-14)
+        eff = copy.copy(robot)
+        eff.arrays = dict(robot.arrays)
+        eff.arrays["link_origin"] = np.ascontiguousarray(out.reshape(robot.arrays["link_origin"].shape))
+        return eff
+
+    def effective_goal_params(self, robot, problem, goal_params, B):
+        """the goal parameters as the reference's goal objects store them (normalising constructors applied)"""
+        gp = self._gp(problem, goal_params, B)
+        out = np.zeros_like(gp)
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.ref_effective_goal_params(C.byref(r), C.byref(p), B, _abi.dptr(gp), _abi.dptr(out)))
+        return out
+
+    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, nthreads=0):
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, n = seeds.shape[0], len(problem.active_variables)
+        gp = self._gp(problem, goal_params, B)
+        rs = np.ascontiguousarray(rng_seeds, dtype=np.uint32)
+        res = dict(solutions=np.zeros((B, robot.n_vars)), fitness=np.zeros(B), success=np.zeros(B, dtype=np.int32), steps=np.zeros(B, dtype=np.int32),
+                   genes=np.zeros((B, 2, 2, n)), gradients=np.zeros((B, 2, 2, n)), species_fitness=np.zeros((B, 2)))
+        r, p = robot.to_abi(), problem.to_abi()
+        nthreads = nthreads or min(B, os.cpu_count() or 1)
+        self._check(self.lib.ref_solve_batch(C.byref(r), C.byref(p), C.byref(cfg), None, B, _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit), 0, nthreads,
+                                             _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["steps"]),
+                                             _abi.dptr(res["genes"]), _abi.dptr(res["gradients"]), _abi.dptr(res["species_fitness"])))
+        return res
+
+    def approx_fitness(self, robot, problem, goal_params, seeds, base, genotypes):
+        """primary, secondary [B][M]; tip frames [B][T][7]; delta frames [B][T][n][7]; approximated frames [B][M][T][7]"""
+        base = np.ascontiguousarray(base, dtype=np.float64).reshape(-1, robot.n_vars)
+        B, n, T = base.shape[0], len(problem.active_variables), len(problem.tip_link_indices)
+        g = np.ascontiguousarray(genotypes, dtype=np.float64).reshape(B, -1, n)
+        M = g.shape[1]
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(B, robot.n_vars)
+        gp = self._gp(problem, goal_params, B)
+        out = dict(primary=np.zeros((B, M)), secondary=np.zeros((B, M)), tips=np.zeros((B, T, 7)), delta=np.zeros((B, T, n, 7)), frames=np.zeros((B, M, T, 7)))
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.ref_approx_fitness_batch(C.byref(r), C.byref(p), B, M, _abi.dptr(gp), _abi.dptr(seeds), _abi.dptr(base), _abi.dptr(g), _abi.dptr(out["primary"]), _abi.dptr(out["secondary"]),
+                                                      _abi.dptr(out["tips"]), _abi.dptr(out["delta"]), _abi.dptr(out["frames"])))
+        return out
