@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,9 @@ struct bioik_ctx
     std::vector<EventPair> pending, pool;
     double ms_evolve = 0, ms_serial = 0;
     int64_t n_evolve = 0, n_serial = 0;
+    int memetic_group = -1; // BIOIK_MEMETIC_GROUP: 0 = memetic step inside the thread-per-task serial kernel, 1 = always k_memetic_group, unset = by problem shape
+    bool serial_split = false; // BIOIK_SERIAL_SPLIT=1: one launch per phase of the serial kernel (phase timing study)
+    double ms_phase[3] = {0, 0, 0};
 };
 
 namespace
@@ -372,8 +376,41 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
             CU(ctx, cudaStreamWaitEvent(se, ctx->ev_fork, 0));
             CU(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         }
+        const int MW = memetic_group_width(P.n);
+        const MemeticGroupKernel mgk = select_memetic_group(MW);
+        const int mg_warps = 4, mg_tasks_per_block = mg_warps * (32 / MW);
+        const GroupLayout mgl{P.n, P.T, P.G, MW};
+        const size_t mg_smem = (size_t)mg_tasks_per_block * mgl.total() * sizeof(double);
+        // the unrolled single-pose path of k_serial issues ~3x fewer instructions per task than a lane group; everything else
+        // gains from the extra parallelism of the group kernel
+        const bool want_mg = ctx->memetic_group < 0 ? !has_unrolled_memetic(P) : ctx->memetic_group != 0;
+        const bool use_mg = want_mg && S.memetic && mg_smem <= 200 * 1024;
+        if(use_mg && mg_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)mgk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
         auto launch_serial = [&](int h, int step, int phases) -> int {
             const int sgrid = (2 * Sh[h].B + pl.block - 1) / pl.block;
+            if(use_mg && (phases & PH_MEMETIC))
+            {
+                // the memetic line search on W lanes per task (bioik_memetic_group.cuh), then the rest of the serial work
+                Timed tg(ctx, ss, 2);
+                mgk<<<(2 * Sh[h].B + mg_tasks_per_block - 1) / mg_tasks_per_block, mg_warps * 32, mg_smem, ss>>>(ctx->hP, Sh[h], step);
+                int r = check_launch(ctx, "k_memetic_group");
+                tg.done();
+                if(r != BIOIK_OK) return r;
+                phases &= ~PH_MEMETIC;
+            }
+            if(ctx->serial_split && phases != PH_PREPARE)
+            {
+                int r = BIOIK_OK;
+                for(int ph = 0; ph < 3 && r == BIOIK_OK; ph++)
+                {
+                    if(!(phases & (1 << ph))) continue;
+                    Timed tp(ctx, ss, 2 + ph);
+                    ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, 1 << ph);
+                    r = check_launch(ctx, "k_serial");
+                    tp.done();
+                }
+                return r;
+            }
             Timed tm(ctx, ss, 1);
             ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, phases);
             int r = check_launch(ctx, "k_serial");
@@ -451,7 +488,10 @@ void drain_events_impl(bioik_ctx* ctx)
             if(p.kind == 0)
                 ctx->ms_evolve += ms, ctx->n_evolve++;
             else
+            {
                 ctx->ms_serial += ms, ctx->n_serial++;
+                if(p.kind >= 2) ctx->ms_phase[p.kind - 2] += ms;
+            }
         }
         ctx->pool.push_back(p);
     }
@@ -522,6 +562,10 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         ctx->use_graphs = !(ng && ng[0] == '1');
         const char* ch = getenv("BIOIK_EVOLVE_CH");
         if(ch && atoi(ch) > 0) ctx->ch_cap = atoi(ch);
+        const char* mg = getenv("BIOIK_MEMETIC_GROUP");
+        ctx->memetic_group = mg ? (mg[0] == '0' ? 0 : 1) : -1;
+        const char* sp = getenv("BIOIK_SERIAL_SPLIT");
+        ctx->serial_split = sp && sp[0] == '1';
         const char* np = getenv("BIOIK_PIPELINE"); // measured slower than the plain sequence on B200 (wave quantisation of the half grids): opt-in
         ctx->pipeline = np && np[0] == '1';
     }
@@ -768,6 +812,9 @@ int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int6
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     CU(ctx, cudaDeviceSynchronize());
     drain_events(ctx);
+    if(ctx->serial_split && ctx->n_serial)
+        fprintf(stderr, "[bioik] serial phases (ms total): memetic %.3f species %.3f prepare %.3f over %lld launches\n", ctx->ms_phase[0], ctx->ms_phase[1], ctx->ms_phase[2], (long long)ctx->n_serial);
+    if(reset) ctx->ms_phase[0] = ctx->ms_phase[1] = ctx->ms_phase[2] = 0;
     ctx->timing = (reset != 2); // the first call switches per-launch timing on; reset == 2 switches it off again
     if(out_ms_evolve) *out_ms_evolve = ctx->ms_evolve;
     if(out_launches_evolve) *out_launches_evolve = ctx->n_evolve;

@@ -69,10 +69,119 @@ inline SerialPlan make_serial_plan(const DProblem& P, int tasks = 0, int sm_coun
     return best;
 }
 
+// problems for which k_serial carries the unrolled register-resident memetic step (memetic_single_pose): one primary
+// PoseGoal, one tip, 6 or 7 genes that all move the tip (the MoveIt plugin's default problem on a 6/7-DOF arm)
+__host__ __device__ inline bool has_unrolled_memetic(const DProblem& P)
+{
+    bool ok = (P.G == 1 && P.T == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary) && (P.n == 6 || P.n == 7);
+    for(int i = 0; ok && i < P.n; i++) ok = (P.genes[i].tipmask & 1) != 0;
+    return ok;
+}
+
 template <class AF, class AT> BIOIK_HD void copy_tips(const DProblem& P, AF frames, AT tips)
 {
     for(int t = 0; t < P.T; t++)
         for(int k = 0; k < 7; k++) tips[7 * t + k] = frames[7 * P.tip_slot[t] + k];
+}
+
+// The memetic line search (src/ik_evolution_2.cpp:436-570) for the plugin's default problem - exactly one primary
+// PoseGoal on one tip, every gene moving that tip - with the gene count as a compile-time constant: genes, gradient,
+// base point, frames and goal parameters live in registers and every loop is unrolled, so the n gradient probes, the
+// two support points and the seven frame components are independent instruction streams the scheduler can overlap
+// (the thread-per-task kernel has about one warp per scheduler, so it lives on instruction-level parallelism).
+// Same operations in the same order as the general loop of k_serial.  Returns nothing; `ind` is updated in place.
+template <int NS, class IndCol, class DeltaColT, class TipCol, class BaseCol, class GpCol>
+BIOIK_HD void memetic_single_pose(const DProblem& P, const DState& S, IndCol ind, DeltaColT delta, TipCol tip0, BaseCol base, GpCol gp, double dp, bool quad)
+{
+    double pg[8], t0r[7], x[NS], bs[NS], gr[NS], tm[NS], cmin[NS], cmax[NS];
+#pragma unroll
+    for(int k = 0; k < 8; k++) pg[k] = gp[k];
+#pragma unroll
+    for(int k = 0; k < 7; k++) t0r[k] = tip0[k];
+#pragma unroll
+    for(int i = 0; i < NS; i++) x[i] = ind[i], bs[i] = base[i], cmin[i] = P.genes[i].clip_min, cmax[i] = P.genes[i].clip_max;
+    const double wsq = P.goals[0].weight_sq;
+    auto full_frames = [&](const double (&g)[NS], double (&F)[7]) {
+#pragma unroll
+        for(int k = 0; k < 7; k++) F[k] = t0r[k];
+#pragma unroll
+        for(int i = 0; i < NS; i++)
+        {
+            const double d = g[i] - bs[i]; // :1086
+            const DeltaColT D = delta + 7 * i;
+#pragma unroll
+            for(int k = 0; k < 7; k++) F[k] = BIOIK_FMA(d, D[k], F[k]);
+        }
+    };
+    auto pose = [&](const double (&F)[7]) { return 0.0 + link_goal_value(G_POSE, pg, F) * wsq; }; // sum = 0.0; sum += e * weight_sq
+    for(int generation = 0; generation < S.memetic_iters; generation++)
+    {
+        double F2[7];
+        full_frames(x, F2);          // :460-462
+        const double f2p = pose(F2); // :463
+        const double fa = f2p + 0.0; // :464 (no secondary goals)
+#pragma unroll
+        for(int i = 0; i < NS; i++) // :465-474
+        {
+            double F3[7];
+            const DeltaColT D = delta + 7 * i;
+#pragma unroll
+            for(int k = 0; k < 7; k++) F3[k] = BIOIK_FMA(dp, D[k], F2[k]); // :469
+            double fb = 0.0;
+            fb += pose(F3);
+            fb += 0.0;
+            gr[i] = fb - fa;
+        }
+        double sum = dp * dp; // :477-482
+#pragma unroll
+        for(int i = 0; i < NS; i++) sum += BIOIK_FABS(gr[i]);
+        const double f = 1.0 / sum * dp;
+#pragma unroll
+        for(int i = 0; i < NS; i++) gr[i] *= f;
+        double FA[7], FB[7];
+#pragma unroll
+        for(int i = 0; i < NS; i++) tm[i] = x[i] - gr[i]; // :485-488
+        full_frames(tm, FA);
+        double f1 = 0.0;
+        f1 += pose(FA);
+        f1 += 0.0;
+        const double f2 = fa;
+#pragma unroll
+        for(int i = 0; i < NS; i++) tm[i] = x[i] + gr[i]; // :492-495
+        full_frames(tm, FB);
+        double f3 = 0.0;
+        f3 += pose(FB);
+        f3 += 0.0;
+        if(quad) // :502-506,:525
+        {
+            double v1 = (f2 - f1);
+            double v2 = (f3 - f2);
+            double v = (v1 + v2) * 0.5;
+            double a = (v1 - v2);
+            double step_size = v / a;
+#pragma unroll
+            for(int i = 0; i < NS; i++) tm[i] = clampd(x[i] + gr[i] * step_size * 1.0, cmin[i], cmax[i]);
+        }
+        else // :549-554
+        {
+            double cost_diff = (f3 - f1) * 0.5;
+            double step_size = f2 / cost_diff;
+#pragma unroll
+            for(int i = 0; i < NS; i++) tm[i] = clampd(x[i] - gr[i] * step_size, cmin[i], cmax[i]);
+        }
+        full_frames(tm, F2); // :526 / :555
+        const double f4p = pose(F2);
+        if(f4p < f2p) // :530-538 / :559-567
+        {
+#pragma unroll
+            for(int i = 0; i < NS; i++) x[i] = tm[i];
+            continue;
+        }
+        else
+            break;
+    }
+#pragma unroll
+    for(int i = 0; i < NS; i++) ind[i] = x[i];
 }
 
 // BS = threads per block (column stride), DS = delta frames in shared memory, FS = link frames in shared memory
@@ -150,7 +259,12 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         // parameters stay in registers; the Pose goal does not read the genes, so the n one-variable evaluations
         // reduce to 7 FMAs + the goal.  Same operations in the same order as the general loop below.
         const bool single_pose = (G == 1 && T == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary);
-        if(single_pose)
+        const bool all_move_tip = has_unrolled_memetic(P);
+        if(all_move_tip && n == 7)
+            memetic_single_pose<7>(P, S, ind, delta, CSC(tip0), CSC(base), CSC(gp), dp, quad);
+        else if(all_move_tip && n == 6)
+            memetic_single_pose<6>(P, S, ind, delta, CSC(tip0), CSC(base), CSC(gp), dp, quad);
+        else if(single_pose)
         {
             double pg[8], t0r[7];
 #pragma unroll

@@ -67,6 +67,7 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     for(int o = 16; o > 0; o >>= 1) acc |= sim_shfl(acc, (int)(threadIdx.x & 31) ^ o);
     return acc;
 }
+static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline double __longlong_as_double(long long v)
 {
@@ -216,7 +217,8 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     {
         // production launch sequence of enqueue_solve(): k_evolve_fast + the fused k_serial (32-thread blocks here)
         SerialPlan pl = make_serial_plan(P);
-        if(use_fast >= 2)
+        const bool group_memetic = use_fast >= 6; // 6 = k_memetic_group + k_serial(SPECIES|PREPARE), the library's default sequence
+        if(use_fast >= 2 && use_fast <= 5)
         {
             // forced placement variant of the serial kernel: 2 = all on chip, 3 = frames local, 4 = delta in HBM, 5 = both off chip
             pl.delta_smem = (use_fast == 2 || use_fast == 3);
@@ -229,7 +231,14 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         for(int step = 0; step < steps; step++)
         {
             launch_warp(2 * B, [&]() { fast(&P, S, step, mtab.data()); });
-            const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
+            int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
+            if(group_memetic && S.memetic)
+            {
+                const int MW = use_fast == 6 ? memetic_group_width(P.n) : (use_fast == 7 ? 8 : (use_fast == 8 ? 16 : 32)); // 7..9 force a width
+                MemeticGroupKernel mgk = select_memetic_group(MW);
+                launch_warp((2 * B + 32 / MW - 1) / (32 / MW), [&]() { mgk(P, S, step); });
+                phases &= ~PH_MEMETIC;
+            }
             launch_warp(sgrid, [&]() { ks(P, S, step, phases); });
         }
     }

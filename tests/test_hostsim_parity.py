@@ -63,6 +63,20 @@ def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B,
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("name,B,pop,mode,steps,variant", [("cfg2", 5, 18, "q", 6, 6), ("cfg2", 3, 40, "l", 4, 6), ("cfg2", 3, 18, "q", 3, 9), ("cfg3", 3, 40, "q", 3, 6), ("cfg3", 1, 20, "q", 2, 7),
+                                                            ("cfg4", 2, 40, "q", 2, 6), ("cfg4", 1, 20, "l", 2, 8), ("cfg5", 3, 36, "q", 2, 6), ("cfg5", 1, 20, "q", 2, 7)])
+def test_group_memetic_kernel(sim, oracle, name, B, pop, mode, steps, variant):
+    """k_memetic_group: the memetic line search on W lanes per task (6 = the width the library picks, 7/8/9 = W forced
+    to 8/16/32, so every problem also runs with more variables than lanes and with idle lanes); odd task counts leave
+    groups of a warp without work."""
+    w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode)
+    a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, fast=variant)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_simulated_fk_and_delta_frames(sim, oracle):
     w = workloads.make("cfg3", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=6)
     tips, delta = sim.fk(w.robot, w.problem, w.targets, delta=True)
