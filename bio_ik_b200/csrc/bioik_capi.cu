@@ -83,6 +83,10 @@ struct bioik_ctx
     double ms_evolve = 0, ms_serial = 0;
     int64_t n_evolve = 0, n_serial = 0;
     int memetic_group = -1; // BIOIK_MEMETIC_GROUP: 0 = memetic step inside the thread-per-task serial kernel, 1 = always k_memetic_group, unset = by problem shape
+    // query-level buffers of bioik_solve_islands
+    double *d_q_gp = nullptr, *d_q_seeds = nullptr, *d_q_sol = nullptr, *d_q_fit = nullptr;
+    int32_t *d_q_succ = nullptr, *d_q_island = nullptr, *d_q_steps = nullptr;
+    int queryQ = 0;
     bool serial_split = false; // BIOIK_SERIAL_SPLIT=1: one launch per phase of the serial kernel (phase timing study)
     double ms_phase[3] = {0, 0, 0};
 };
@@ -583,6 +587,7 @@ void bioik_destroy(bioik_ctx* ctx)
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
+    cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
     if(ctx->stream_evolve) cudaStreamDestroy(ctx->stream_evolve);
     if(ctx->stream_serial) cudaStreamDestroy(ctx->stream_serial);
@@ -617,6 +622,7 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     ctx->d_rs = nullptr;
     ctx->d_osucc = ctx->d_osteps = nullptr;
     ctx->stageB = 0;
+    ctx->queryQ = 0;
     ctx->sched_steps = -1;
     if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
     ctx->graph_B = -1;
@@ -692,6 +698,58 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     if(out_fitness) CU(ctx, cudaMemcpyAsync(out_fitness, ctx->d_ofit, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if(out_success) CU(ctx, cudaMemcpyAsync(out_success, ctx->d_osucc, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_osteps, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return BIOIK_OK;
+}
+
+int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap, double* out_solutions,
+                        double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    if(Q <= 0 || islands <= 0 || !seeds || !rng_seeds || !out_solutions || (int64_t)Q * islands > (int64_t)INT32_MAX / 4) return fail(ctx, BIOIK_E_INVALID, "bad solve_islands arguments");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const int B = Q * islands;
+    int rc = ensure_staging(ctx, B);
+    if(rc != BIOIK_OK) return rc;
+    const DProblem& P = ctx->hP;
+    cudaStream_t st = ctx->stream;
+    if(Q > ctx->queryQ)
+    {
+        CU(ctx, cudaStreamSynchronize(st));
+        cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
+        ctx->queryQ = 0;
+        CU(ctx, cudaMalloc(&ctx->d_q_gp, (size_t)Q * P.G * GOAL_NPARAM * 8 + 8));
+        CU(ctx, cudaMalloc(&ctx->d_q_seeds, (size_t)Q * P.n_vars * 8));
+        CU(ctx, cudaMalloc(&ctx->d_q_sol, (size_t)Q * P.n_vars * 8));
+        CU(ctx, cudaMalloc(&ctx->d_q_fit, (size_t)Q * 8));
+        CU(ctx, cudaMalloc(&ctx->d_q_succ, (size_t)Q * 4));
+        CU(ctx, cudaMalloc(&ctx->d_q_island, (size_t)Q * 4));
+        CU(ctx, cudaMalloc(&ctx->d_q_steps, (size_t)Q * 4));
+        ctx->queryQ = Q;
+    }
+    const int per_gp = P.G * GOAL_NPARAM, per_seed = P.n_vars;
+    if(goal_params) CU(ctx, cudaMemcpyAsync(ctx->d_q_gp, goal_params, (size_t)Q * per_gp * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_q_seeds, seeds, (size_t)Q * per_seed * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_rs, rng_seeds, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    {
+        const size_t total = (size_t)B * std::max(per_gp, per_seed);
+        k_expand_islands<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, islands, per_gp, per_seed, goal_params ? ctx->d_q_gp : nullptr, ctx->d_q_seeds, ctx->d_gp, ctx->d_seeds);
+        if((rc = check_launch(ctx, "k_expand_islands")) != BIOIK_OK) return rc;
+    }
+    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr; // the staging buffers are shared with the cached solve_batch graph
+    ctx->graph_B = -1;
+    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+    if(rc != BIOIK_OK) return rc;
+    // without per-query parameters enqueue_solve has broadcast the defaults into d_gp
+    k_select_islands<<<(Q + 127) / 128, 128, 0, st>>>(ctx->dP, Q, islands, ctx->d_gp, ctx->d_seeds, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps, wrap, ctx->d_q_sol, ctx->d_q_fit, ctx->d_q_succ, ctx->d_q_island,
+                                                      ctx->d_q_steps);
+    if((rc = check_launch(ctx, "k_select_islands")) != BIOIK_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(out_solutions, ctx->d_q_sol, (size_t)Q * P.n_vars * 8, cudaMemcpyDeviceToHost, st));
+    if(out_fitness) CU(ctx, cudaMemcpyAsync(out_fitness, ctx->d_q_fit, (size_t)Q * 8, cudaMemcpyDeviceToHost, st));
+    if(out_success) CU(ctx, cudaMemcpyAsync(out_success, ctx->d_q_succ, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+    if(out_island) CU(ctx, cudaMemcpyAsync(out_island, ctx->d_q_island, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
+    if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_q_steps, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return BIOIK_OK;
 }

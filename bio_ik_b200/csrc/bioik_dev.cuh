@@ -26,6 +26,8 @@
 #define BIOIK_FABS(x) std::fabs(x)
 #define BIOIK_FMIN(a, b) std::fmin((a), (b))
 #define BIOIK_FMAX(a, b) std::fmax((a), (b))
+#define BIOIK_FLOOR(x) std::floor(x)
+#define BIOIK_CEIL(x) std::ceil(x)
 #define BIOIK_ATAN2(a, b) std::atan2((a), (b))
 #define BIOIK_ACOS(a) std::acos(a)
 static inline double bioik_clear_low_word(double s)
@@ -46,6 +48,8 @@ static inline double bioik_clear_low_word(double s)
 #define BIOIK_FABS(x) fabs(x)
 #define BIOIK_FMIN(a, b) fmin((a), (b))
 #define BIOIK_FMAX(a, b) fmax((a), (b))
+#define BIOIK_FLOOR(x) floor(x)
+#define BIOIK_CEIL(x) ceil(x)
 #define BIOIK_ATAN2(a, b) atan2((a), (b))
 #define BIOIK_ACOS(a) acos(a)
 #define BIOIK_CLEAR_LOW_WORD(s) __hiloint2double(__double2hiint(s), 0)
@@ -111,6 +115,7 @@ struct DProblem
     DMimic mimics[MAX_VARS];
     int32_t dep_slot[MAX_SLOTS + MAX_GENES];
     double dep_scale[MAX_SLOTS + MAX_GENES];
+    int32_t wrap_gene[MAX_GENES]; // 1: the plugin's angle wrap applies (revolute variable, robot without mimic joints; kinematics_plugin.cpp:583-584)
 };
 
 // ---------------------------------------------------------------------------
@@ -624,6 +629,66 @@ BIOIK_HD double goal_fitness(const DProblem& P, int which, const double* gp, con
         sum += goal_value(P, P.goals[g], gp + g * GOAL_NPARAM, tips, x, seed) * P.goals[g].weight_sq;
     }
     return sum;
+}
+
+// ---------------------------------------------------------------------------
+// What the MoveIt plugin does with the solver's answer (src/kinematics_plugin.cpp:580-611): revolute variables are
+// moved by multiples of 2 pi next to the initial guess, wrapped back inside their limits and clamped.
+// v = solution value, r = initial guess, [lo, hi] = RobotInfo::getMin/getMax.
+// ---------------------------------------------------------------------------
+BIOIK_HD double wrap_angle(double v, double r, double lo, double hi)
+{
+    const double pi = 3.14159265358979323846;
+    if(r < v - pi || r > v + pi) // move close to initial guess (:590-598)
+    {
+        v -= r;
+        v /= (2 * pi);
+        v += 0.5;
+        v -= BIOIK_FLOOR(v);
+        v -= 0.5;
+        v *= (2 * pi);
+        v += r;
+    }
+    if(v > hi) v -= BIOIK_CEIL(BIOIK_FMAX(0.0, v - hi) / (2 * pi)) * (2 * pi); // wrap at joint limits (:601-604)
+    if(v < lo) v += BIOIK_CEIL(BIOIK_FMAX(0.0, lo - v) / (2 * pi)) * (2 * pi);
+    if(v < lo) v = lo; // clamp at edges (:607-610)
+    if(v > hi) v = hi;
+    return v;
+}
+
+// IKParallel::solve's choice among its solver threads (src/ik_parallel.h:218-258), here among the `islands`
+// differently seeded runs of one query: the successful island with the smallest primary (+ secondary, if the problem
+// has secondary goals) fitness; if none succeeded, the smallest primary fitness.  Strict '<' scans in island order.
+// sol: [islands][n_vars] full variable vectors, fit / succ: [islands].  Returns the island; *best = best_fitness.
+template <class AP> BIOIK_HD int select_island(const DProblem& P, int islands, AP gp, const double* seed, const double* sol, const double* fit, const int32_t* succ, double* best)
+{
+    int best_index = 0;
+    double best_fitness = DBLMAX;
+    for(int i = 0; i < islands; i++)
+    {
+        if(!succ[i]) continue;
+        double fitness = fit[i];
+        if(P.has_secondary)
+        {
+            double x[MAX_GENES];
+            for(int g = 0; g < P.n; g++) x[g] = sol[(size_t)i * P.n_vars + P.genes[g].var]; // extractActiveVariables
+            fitness = fit[i] + goal_fitness_secondary(P, gp, (const double*)x, seed);
+        }
+        if(fitness < best_fitness)
+        {
+            best_fitness = fitness;
+            best_index = i;
+        }
+    }
+    if(best_fitness == DBLMAX)
+        for(int i = 0; i < islands; i++)
+            if(fit[i] < best_fitness)
+            {
+                best_fitness = fit[i];
+                best_index = i;
+            }
+    *best = best_fitness;
+    return best_index;
 }
 
 // ---------------------------------------------------------------------------

@@ -239,6 +239,16 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
                 Gn.dep_count++;
             }
     }
+    {
+        // kinematics_plugin.cpp:583-584: the angle wrap applies to revolute variables of robots without mimic joints
+        bool any_mimic = false;
+        for(int l = 0; l < R.n_links; l++) any_mimic = any_mimic || R.mimic[l] >= 0;
+        for(int i = 0; i < p->n_active; i++)
+        {
+            int j = R.var_joint[p->active_vars[i]];
+            P.wrap_gene[i] = (!any_mimic && j >= 0 && R.jtype[j] == BIOIK_JOINT_REVOLUTE) ? 1 : 0;
+        }
+    }
     for(int i = 0; i < p->n_active; i++) rcp_sum += rcp[i];
     for(int i = 0; i < p->n_active; i++) P.genes[i].vel_weight = rcp_sum > 0 ? rcp[i] / rcp_sum : 1.0 / p->n_active;
     // goals

@@ -538,6 +538,54 @@ __global__ void k_finalize(const DProblem* __restrict__ Pp, DState S, double* ou
 }
 
 // ---------------------------------------------------------------------------
+// Many differently seeded islands of ONE query: the batch holds Q x islands runs,
+// run q * islands + k being island k of query q.
+// ---------------------------------------------------------------------------
+// island inputs from query inputs: goal parameters [Q][G][NPARAM] and seeds [Q][n_vars] repeated `islands` times
+__global__ void k_expand_islands(int Q, int islands, int per_gp, int per_seed, const double* gp, const double* seeds, double* gp_out, double* seeds_out)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ngp = gp ? (size_t)Q * islands * per_gp : 0, nsd = (size_t)Q * islands * per_seed;
+    if(idx < ngp)
+    {
+        const size_t b = idx / per_gp, k = idx - b * per_gp;
+        gp_out[idx] = gp[(b / islands) * per_gp + k];
+    }
+    if(idx < nsd)
+    {
+        const size_t b = idx / per_seed, k = idx - b * per_seed;
+        seeds_out[idx] = seeds[(b / islands) * per_seed + k];
+    }
+}
+
+// IKParallel::solve's selection among its threads (src/ik_parallel.h:218-258) + the plugin's angle wrap
+// (src/kinematics_plugin.cpp:580-611) for query q; inputs are the per-run outputs of k_finalize.
+__global__ void k_select_islands(const DProblem* __restrict__ Pp, int Q, int islands, const double* goal_params, const double* seeds, const double* sol, const double* fit, const int32_t* succ, const int32_t* steps, int wrap,
+                                 double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    const DProblem& P = *Pp;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= Q) return;
+    const size_t b0 = (size_t)q * islands;
+    const double* seed = seeds + b0 * P.n_vars;       // every island of the query has the query's seed
+    const double* gp = goal_params + b0 * P.G * GOAL_NPARAM;
+    double best;
+    const int k = select_island(P, islands, gp, seed, sol + b0 * P.n_vars, fit + b0, succ + b0, &best);
+    const double* s = sol + (b0 + k) * P.n_vars;
+    for(int v = 0; v < P.n_vars; v++)
+    {
+        double x = s[v];
+        const int g = P.gene_of_var[v];
+        if(wrap && g >= 0 && P.wrap_gene[g]) x = wrap_angle(x, seed[v], P.genes[g].vmin, P.genes[g].vmax);
+        out_solutions[(size_t)q * P.n_vars + v] = x;
+    }
+    if(out_fitness) out_fitness[q] = best;
+    if(out_success) out_success[q] = succ[b0 + k];
+    if(out_island) out_island[q] = k;
+    if(out_steps) out_steps[q] = steps[b0 + k];
+}
+
+// ---------------------------------------------------------------------------
 // component kernels (parity tests of the individual rows of SURVEY.md §8(a))
 // ---------------------------------------------------------------------------
 __global__ void k_fk_batch(const DProblem* __restrict__ Pp, int B, const double* variables, double* out_tips)

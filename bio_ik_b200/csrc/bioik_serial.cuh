@@ -78,6 +78,31 @@ __host__ __device__ inline bool has_unrolled_memetic(const DProblem& P)
     return ok;
 }
 
+// asynchronous 8-byte global -> shared copies (LDGSTS): a thread queues every input of its task back to back and waits
+// once, instead of paying one memory round trip per load-store pair of a staging loop
+BIOIK_HD void stage8(double* dst_shared, const double* src_global)
+{
+#ifdef BIOIK_HOSTSIM
+    *dst_shared = *src_global;
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src_global) : "memory");
+#endif
+}
+BIOIK_HD void stage_wait()
+{
+#ifndef BIOIK_HOSTSIM
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+// assemble_variables when the non-gene entries of `vars` already hold the seed: gene entries, then updateMimic
+template <class AG, class AV> BIOIK_HD void assemble_genes(const DProblem& P, AG genes, AV vars)
+{
+    for(int i = 0; i < P.n; i++) vars[P.genes[i].var] = genes[i];
+    for(int m = 0; m < P.n_mimic; m++) vars[P.mimics[m].dest] = vars[P.mimics[m].src] * P.mimics[m].factor + P.mimics[m].offset;
+}
+
 template <class AF, class AT> BIOIK_HD void copy_tips(const DProblem& P, AF frames, AT tips)
 {
     for(int t = 0; t < P.T; t++)
@@ -223,12 +248,38 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         frames.p = lf;
 
     const double* seed = S.seeds + (size_t)q * P.n_vars;
+    const bool do_memetic = active && (phases & PH_MEMETIC) && S.memetic;
+    const bool unrolled = has_unrolled_memetic(P);
+    // individual 1 and the two gradient vectors only pass through the species block; they can be fetched up front
+    // unless the general memetic loop below needs temp / grad as scratch
+    const bool species_prefetch = active && (phases & PH_SPECIES) && (!do_memetic || unrolled);
     if(active)
     {
         const double* g = S.goal_params + (size_t)q * G * GOAL_NPARAM;
-        for(int k = 0; k < G * GOAL_NPARAM; k++) gp[k] = g[k];
+        for(int k = 0; k < G * GOAL_NPARAM; k++) stage8(&gp[k], g + k);
         const double* gi = S.genes + ((size_t)task * 2 + 0) * n;
-        for(int i = 0; i < n; i++) ind[i] = gi[i];
+        for(int i = 0; i < n; i++) stage8(&ind[i], gi + i);
+        for(int v = 0; v < P.n_vars; v++) stage8(&vars[v], seed + v); // non-gene variables stay at the seed (genesToJointVariables)
+        if(do_memetic)
+        {
+            const double* t0 = S.tip0 + (size_t)task * T * 7;
+            for(int k = 0; k < 7 * T; k++) stage8(&tip0[k], t0 + k);
+            const double* b0 = S.base + (size_t)task * n;
+            for(int i = 0; i < n; i++) stage8(&base[i], b0 + i);
+            if(DS)
+            {
+                const double* d0 = S.delta + (size_t)task * T * n * 7;
+                for(int k = 0; k < 7 * T * n; k++) stage8(&delta[k], d0 + k);
+            }
+        }
+        if(species_prefetch)
+        {
+            const double* g1 = S.genes + ((size_t)task * 2 + 1) * n;
+            const double* r0 = S.grads + ((size_t)task * 2 + 0) * n;
+            const double* r1 = S.grads + ((size_t)task * 2 + 1) * n;
+            for(int i = 0; i < n; i++) stage8(&temp[i], g1 + i), stage8(&grad[i], r0 + i), stage8(&stash[i], r1 + i);
+        }
+        stage_wait();
     }
     const CSC cgp = gp;
 
@@ -239,19 +290,8 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
     //   e = n+1      x = genes - gradient         full -> ph3                 f1             (:485-488)
     //   e = n+2      x = genes + gradient         full -> ph3                 f3             (:492-495)
     //   e = n+3      x = clip(genes +- gradient * step)  full -> ph2          f4p (primary)  (:525-527 / :554-556)
-    if(active && (phases & PH_MEMETIC) && S.memetic)
+    if(do_memetic)
     {
-        {
-            const double* t0 = S.tip0 + (size_t)task * T * 7;
-            for(int k = 0; k < 7 * T; k++) tip0[k] = t0[k];
-            const double* b0 = S.base + (size_t)task * n;
-            for(int i = 0; i < n; i++) base[i] = b0[i];
-            if(DS)
-            {
-                const double* d0 = S.delta + (size_t)task * T * n * 7;
-                for(int k = 0; k < 7 * T * n; k++) delta[k] = d0[k];
-            }
-        }
         double dp = 0.0000001;                                                                                // :450
         if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
         const bool quad = S.memetic == 'q';
@@ -259,7 +299,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         // parameters stay in registers; the Pose goal does not read the genes, so the n one-variable evaluations
         // reduce to 7 FMAs + the goal.  Same operations in the same order as the general loop below.
         const bool single_pose = (G == 1 && T == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary);
-        const bool all_move_tip = has_unrolled_memetic(P);
+        const bool all_move_tip = unrolled;
         if(all_move_tip && n == 7)
             memetic_single_pose<7>(P, S, ind, delta, CSC(tip0), CSC(base), CSC(gp), dp, quad);
         else if(all_move_tip && n == 6)
@@ -429,8 +469,8 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
         double f = 0.0;
         if(active)
         {
-            assemble_variables(P, seed, CSC(ind), vars); // genesToJointVariables :610
-            exact_fk(P, CSC(vars), frames);               // computeFitness :611 -> applyConfiguration
+            assemble_genes(P, CSC(ind), vars); // genesToJointVariables :610
+            exact_fk(P, CSC(vars), frames);     // computeFitness :611 -> applyConfiguration
             copy_tips(P, frames, ph2);
             f = goal_fitness_t(P, 0, cgp, CSC(ph2), CSC(ind), seed);
             frames_valid = true;
@@ -448,12 +488,13 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
             const double* g1 = S.genes + ((size_t)task * 2 + 1) * n;
             const double* r0 = S.grads + ((size_t)task * 2 + 0) * n;
             const double* r1 = S.grads + ((size_t)task * 2 + 1) * n;
-            for(int i = 0; i < n; i++)
-            {
-                temp[i] = g1[i];
-                grad[i] = r0[i];
-                stash[i] = r1[i];
-            }
+            if(!species_prefetch)
+                for(int i = 0; i < n; i++)
+                {
+                    temp[i] = g1[i];
+                    grad[i] = r0[i];
+                    stash[i] = r1[i];
+                }
         }
         __syncwarp(); // both species of a query have read their state
         if(active)
@@ -504,7 +545,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
                     {
                         const double* sol = S.sol + (size_t)q * n;
                         for(int i = 0; i < n; i++) base[i] = sol[i];
-                        assemble_variables(P, seed, CSC(base), vars);
+                        assemble_genes(P, CSC(base), vars);
                         exact_fk(P, CSC(vars), frames);
                         copy_tips(P, frames, ph3);
                         frames_valid = false;
@@ -540,7 +581,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
     if(active && (phases & PH_PREPARE))
     {
         // p_variables = post-mimic variables of the base configuration (:1063)
-        assemble_variables(P, seed, CSC(ind), vars);
+        assemble_genes(P, CSC(ind), vars);
         if(!frames_valid) exact_fk(P, CSC(vars), frames);
         double* t0 = S.tip0 + (size_t)my_task * T * 7;
         for(int t = 0; t < T; t++)

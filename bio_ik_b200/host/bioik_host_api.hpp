@@ -441,6 +441,23 @@ public:
               "bioik_solve_batch");
         return r;
     }
+    struct IslandResult
+    {
+        std::vector<double> solutions, fitness;
+        std::vector<int32_t> success, island, steps;
+    };
+    // Q MoveIt-style queries, `islands` differently seeded runs each, reduced like IKParallel::solve (src/ik_parallel.h:218-258)
+    // and angle-wrapped like the plugin (src/kinematics_plugin.cpp:580-611).  rng_seeds: [Q * islands].
+    IslandResult solveIslands(const std::vector<double>& goal_params, const std::vector<double>& seeds, int islands, const std::vector<uint32_t>& rng_seeds, int steps, bool early_exit = true, bool wrap = true)
+    {
+        int Q = (int)(rng_seeds.size() / (size_t)islands);
+        IslandResult r;
+        r.solutions.resize((size_t)Q * n_vars_), r.fitness.resize(Q), r.success.resize(Q), r.island.resize(Q), r.steps.resize(Q);
+        check(bioik_solve_islands(ctx_, Q, islands, goal_params.empty() ? nullptr : goal_params.data(), seeds.data(), rng_seeds.data(), steps, early_exit, wrap, r.solutions.data(), r.fitness.data(), r.success.data(),
+                                  r.island.data(), r.steps.data()),
+              "bioik_solve_islands");
+        return r;
+    }
     std::vector<double> forwardKinematics(const std::vector<double>& variables, int n_tips)
     {
         int B = (int)(variables.size() / n_vars_);

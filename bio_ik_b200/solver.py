@@ -77,6 +77,21 @@ class IKSolver:
                                                _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["steps"])))
         return res
 
+    def solve_islands(self, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=False, wrap=True):
+        """Q MoveIt-style queries, each solved by `islands` differently seeded runs in one batch and reduced like
+        IKParallel::solve reduces its threads (src/ik_parallel.h:218-258: best successful island by primary +
+        secondary fitness, else best primary fitness); wrap=True applies the plugin's angle wrap towards the seed
+        (src/kinematics_plugin.cpp:580-611).  rng_seeds: [Q * islands] (default 1 + run index)."""
+        rm, pr = self.robot_model, self.problem
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, rm.n_vars)
+        Q = seeds.shape[0]
+        gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(Q, pr.n_goals, _abi.GOAL_NPARAM)
+        rs = (1 + np.arange(Q * islands)).astype(np.uint32) if rng_seeds is None else np.ascontiguousarray(rng_seeds, dtype=np.uint32).reshape(Q * islands)
+        res = dict(solutions=np.empty((Q, rm.n_vars)), fitness=np.empty(Q), success=np.empty(Q, dtype=np.int32), island=np.empty(Q, dtype=np.int32), steps=np.empty(Q, dtype=np.int32))
+        self._check(self.lib.bioik_solve_islands(self._ctx, Q, int(islands), _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit), int(wrap), _abi.dptr(res["solutions"]),
+                                                 _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
+        return res
+
     def solve_batch_device(self, B, d_goal_params, d_seeds, d_rng_seeds, steps, early_exit, d_solutions, d_fitness, d_success, d_steps, stream=None):
         """Same with raw device pointers (ints); enqueues on `stream` (or the context stream), no sync."""
         self._check(self.lib.bioik_solve_batch_device(self._ctx, B, d_goal_params, d_seeds, d_rng_seeds, steps, int(early_exit), d_solutions, d_fitness, d_success, d_steps, stream))

@@ -202,6 +202,28 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
                             double* out_species_fitness, double* out_solutions,
                             double* out_fitness);
 
+/* One MoveIt-style query solved by many differently seeded islands at once, then reduced the way the reference
+ * reduces its solver threads:
+ *   - run q * islands + k is island k of query q: the query's goal parameters and seed, rng_seeds[q * islands + k];
+ *     the reference's IKParallel starts identical clones on every thread (src/ik_parallel.h:119-127) - the island
+ *     seeds are what makes the extra runs worth something;
+ *   - selection = IKParallel::solve (src/ik_parallel.h:218-258): among the successful islands the smallest
+ *     primary (+ secondary, when the problem has secondary goals) fitness, else the smallest primary fitness;
+ *     first island wins ties;
+ *   - wrap != 0 applies the plugin's angle wrap to the selected solution (src/kinematics_plugin.cpp:580-611):
+ *     revolute variables of robots without mimic joints are moved by multiples of 2 pi next to the seed, wrapped
+ *     inside [min, max] and clamped.  (MoveIt's enforcePositionBounds, :614, is MoveIt code and not applied.)
+ * Host pointers.
+ *   goal_params   [Q][n_goals][BIOIK_GOAL_NPARAM] or NULL      seeds       [Q][n_vars]
+ *   rng_seeds     [Q * islands]
+ *   out_solutions [Q][n_vars]   out_fitness [Q] (IKParallel::getSolutionFitness: incl. secondary when successful)
+ *   out_success   [Q]           out_island  [Q] index of the selected island   out_steps [Q] its step() calls
+ * Any output except out_solutions may be NULL. */
+int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds,
+                        const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap,
+                        double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island,
+                        int32_t* out_steps);
+
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 int64_t bioik_launch_count(const bioik_ctx* ctx);
 

@@ -1513,4 +1513,77 @@ inline QueryResult solveQuery(const RobotModel& robot, const Tables& tables, con
     return res;
 }
 
+// ---------------------------------------------------------------------------
+// After the solver: what IKParallel and the MoveIt plugin do with per-thread results.
+// ---------------------------------------------------------------------------
+// src/ik_parallel.h:218-258 — choice among `count` solver results of one problem (threads in the reference, islands
+// in the batch build).  solutions: full variable vectors; fitness: primary fitness of each (ik_parallel.h:181).
+inline size_t selectBestResult(Problem& problem, const std::vector<std::vector<double>>& solutions, const std::vector<double>& fitness, const std::vector<int>& success, double& best_fitness)
+{
+    size_t count = solutions.size(), best_index = 0;
+    best_fitness = DBL_MAX;
+    std::vector<Frame> null_tip_frames(problem.tip_link_indices.size());
+    for(size_t i = 0; i < count; i++) // :224-248
+    {
+        if(success[i])
+        {
+            double f;
+            if(problem.secondary_goals.empty())
+                f = fitness[i];
+            else
+            {
+                std::vector<double> active(problem.active_variables.size());
+                for(size_t k = 0; k < active.size(); k++) active[k] = solutions[i][problem.active_variables[k]]; // extractActiveVariables
+                f = fitness[i] + problem.computeGoalFitness(problem.secondary_goals, null_tip_frames.data(), active.data());
+            }
+            if(f < best_fitness)
+            {
+                best_fitness = f;
+                best_index = i;
+            }
+        }
+    }
+    if(best_fitness == DBL_MAX) // :252-262
+        for(size_t i = 0; i < count; i++)
+            if(fitness[i] < best_fitness)
+            {
+                best_fitness = fitness[i];
+                best_index = i;
+            }
+    return best_index;
+}
+
+// src/kinematics_plugin.cpp:580-611 — angle wrap of the returned state (in place)
+inline void wrapAngles(const RobotModel& robot, const Problem& problem, std::vector<double>& state)
+{
+    bool has_mimic = false;
+    for(auto& l : robot.links) has_mimic = has_mimic || l.mimic >= 0;
+    for(auto ivar : problem.active_variables)
+    {
+        auto v = state[ivar];
+        int j = robot.var_joint[ivar];
+        if(j >= 0 && robot.links[j].joint_type == REVOLUTE && !has_mimic) // :583-584
+        {
+            auto r = problem.initial_guess[ivar];
+            auto lo = problem.modelInfo.getMin(ivar);
+            auto hi = problem.modelInfo.getMax(ivar);
+            if(r < v - M_PI || r > v + M_PI) // :590-598
+            {
+                v -= r;
+                v /= (2 * M_PI);
+                v += 0.5;
+                v -= std::floor(v);
+                v -= 0.5;
+                v *= (2 * M_PI);
+                v += r;
+            }
+            if(v > hi) v -= std::ceil(std::max(0.0, v - hi) / (2 * M_PI)) * (2 * M_PI); // :601-604
+            if(v < lo) v += std::ceil(std::max(0.0, lo - v) / (2 * M_PI)) * (2 * M_PI);
+            if(v < lo) v = lo; // :607-610
+            if(v > hi) v = hi;
+        }
+        state[ivar] = v;
+    }
+}
+
 } // namespace bioik_oracle

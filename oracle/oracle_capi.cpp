@@ -394,5 +394,48 @@ int oracle_solve_batch(const BioikRobot* robot, const BioikProblem* problem, con
     }
 }
 
+// IKParallel's result selection (src/ik_parallel.h:218-258) over the `islands` runs of each of Q queries + the plugin's
+// angle wrap (src/kinematics_plugin.cpp:580-611); same contract as bioik_solve_islands' reduction step.
+// goal_params [Q*islands][G][NPARAM] or NULL, seeds [Q*islands][n_vars], run inputs sol [Q*islands][n_vars], fit, succ, steps.
+int oracle_select_islands(const BioikRobot* robot, const BioikProblem* problem, int Q, int islands, const double* goal_params, const double* seeds, const double* sol, const double* fit, const int32_t* succ, const int32_t* steps, int wrap,
+                          double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    try
+    {
+        RobotModel rm = makeRobot(robot);
+        Problem pr0 = makeProblem(rm, problem);
+        for(int q = 0; q < Q; q++)
+        {
+            size_t b0 = (size_t)q * islands;
+            Problem pr = pr0;
+            applyQuery(pr, problem, goal_params ? goal_params + b0 * problem->n_goals * GOAL_NPARAM : nullptr, seeds + b0 * rm.n_vars, rm.n_vars);
+            std::vector<std::vector<double>> sols(islands);
+            std::vector<double> f(islands);
+            std::vector<int> ok(islands);
+            for(int k = 0; k < islands; k++)
+            {
+                sols[k].assign(sol + (b0 + k) * rm.n_vars, sol + (b0 + k + 1) * rm.n_vars);
+                f[k] = fit[b0 + k];
+                ok[k] = succ[b0 + k];
+            }
+            double best;
+            size_t k = selectBestResult(pr, sols, f, ok, best);
+            std::vector<double> state = sols[k];
+            if(wrap) wrapAngles(rm, pr, state);
+            std::copy(state.begin(), state.end(), out_solutions + (size_t)q * rm.n_vars);
+            if(out_fitness) out_fitness[q] = best;
+            if(out_success) out_success[q] = ok[k];
+            if(out_island) out_island[q] = (int32_t)k;
+            if(out_steps) out_steps[q] = steps ? steps[b0 + k] : 0;
+        }
+        return 0;
+    }
+    catch(std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 int oracle_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 }

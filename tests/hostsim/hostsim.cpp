@@ -258,6 +258,29 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     return 0;
 }
 
+// k_select_islands on host memory (the reduction step of bioik_solve_islands)
+int hostsim_select_islands(const BioikRobot* robot, const BioikProblem* problem, int Q, int islands, const double* goal_params, const double* seeds, const double* sol, const double* fit, const int32_t* succ, const int32_t* steps, int wrap,
+                           double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    HostRobot R;
+    int rc = intake_robot(robot, R, g_err);
+    if(rc) return rc;
+    static DProblem P;
+    rc = build_problem(R, problem, P, g_err);
+    if(rc) return rc;
+    std::vector<double> gp_default;
+    if(!goal_params)
+    {
+        gp_default.resize((size_t)Q * islands * P.G * GOAL_NPARAM);
+        for(int b = 0; b < Q * islands; b++)
+            for(int g = 0; g < P.G; g++)
+                for(int k = 0; k < GOAL_NPARAM; k++) gp_default[((size_t)b * P.G + g) * GOAL_NPARAM + k] = problem->goals[g].p[k];
+        goal_params = gp_default.data();
+    }
+    launch_serial((Q + 127) / 128, 128, [&]() { k_select_islands(&P, Q, islands, goal_params, seeds, sol, fit, succ, steps, wrap, out_solutions, out_fitness, out_success, out_island, out_steps); });
+    return 0;
+}
+
 int hostsim_fk(const BioikRobot* robot, const BioikProblem* problem, int B, const double* variables, double* out_tips, double* out_delta)
 {
     HostRobot R;

@@ -23,6 +23,7 @@ class HostSim:
         lib.hostsim_sincos.argtypes = [C.c_int, dp, dp, dp]
         lib.hostsim_solve.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_int, dp, dp, up, C.c_int, C.c_int,
                                       dp, dp, ip, ip, dp, dp, dp, C.c_int]
+        lib.hostsim_select_islands.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp, dp, ip, ip, C.c_int, dp, dp, ip, ip, ip]
         lib.hostsim_fk.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, dp, dp, dp]
 
     def _check(self, rc):
@@ -50,3 +51,16 @@ class HostSim:
         r, p = robot.to_abi(), problem.to_abi()
         self._check(self.lib.hostsim_fk(C.byref(r), C.byref(p), B, _abi.dptr(v), _abi.dptr(tips), _abi.dptr(d)))
         return (tips, d) if delta else tips
+
+    def select_islands(self, robot, problem, islands, goal_params, seeds, runs, wrap=True):
+        """k_select_islands on the per-run results `runs` (dict of solutions / fitness / success / steps of Q * islands runs)"""
+        B = len(runs["fitness"])
+        Q = B // islands
+        gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
+        sd = np.ascontiguousarray(seeds, dtype=np.float64).reshape(B, robot.n_vars)
+        sol, fit, succ, stp = (np.ascontiguousarray(runs[k]) for k in ("solutions", "fitness", "success", "steps"))
+        res = dict(solutions=np.zeros((Q, robot.n_vars)), fitness=np.zeros(Q), success=np.zeros(Q, dtype=np.int32), island=np.zeros(Q, dtype=np.int32), steps=np.zeros(Q, dtype=np.int32))
+        r, p = robot.to_abi(), problem.to_abi()
+        self._check(self.lib.hostsim_select_islands(C.byref(r), C.byref(p), Q, islands, _abi.dptr(gp), _abi.dptr(sd), _abi.dptr(sol), _abi.dptr(fit), _abi.iptr(succ), _abi.iptr(stp), int(wrap),
+                                                    _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
+        return res

@@ -289,3 +289,40 @@ def test_mimic_joints_on_gpu(oracle):
     ref = oracle.solve(rm, pr, cfg, gp, seeds, rs, 12)
     solver = IKSolver(rm, population=64).initialize(pr)
     gpu_util.assert_bit_equal(solver.trace(gp, seeds, rs, 12), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# islands of one query, IKParallel's selection, the plugin's angle wrap
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,Q,islands,steps,early", [("cfg2", 24, 8, 12, False), ("cfg2", 16, 5, 25, True), ("cfg4", 6, 4, 6, False), ("cfg3", 8, 3, 6, False)])
+def test_solve_islands_matches_the_oracle(oracle, name, Q, islands, steps, early):
+    w = workloads.make(name, ofk(oracle), batch=Q)
+    solver = IKSolver(w.robot, mode="bio2_memetic", population=40, random_seed=1, device=0).initialize(w.problem)
+    cfg = oracle_lib.make_cfg(population=40)
+    for wrap in (True, False):
+        got = solver.solve_islands(w.goal_params, w.seeds, islands, steps, early_exit=early, wrap=wrap)
+        ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=early, wrap=wrap)
+        for k in ("solutions", "fitness", "success", "island", "steps"):
+            assert np.array_equal(got[k], ref[k]), (k, wrap)
+    if steps >= 12:
+        # islands share the table-driven mutation stream (fixed-seed XORShift64 index, src/ik_base.h:118-125); their own
+        # minstd engine only enters through the wipeout of the second species, so they need a few steps to part ways
+        assert len(set(ref["island"].tolist())) > 1
+    # a batch solve afterwards still works (the staging buffers are shared)
+    a = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 3)
+    b = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 3)
+    assert np.array_equal(a["solutions"], b["solutions"])
+
+
+def test_solve_islands_default_goal_parameters_and_seeds(oracle):
+    rm, groups = robots.pr2_like()
+    g = groups["right_arm"]
+    pr = Problem().initialize(rm, g, [G.PoseGoal("r_wrist_roll_link", (0.55, -0.25, 0.95), (0.0, 0.0, 0.0, 1.0)), G.MinimalDisplacementGoal(0.3)])
+    solver = IKSolver(rm, mode="bio2_memetic", population=32, random_seed=1, device=0).initialize(pr)
+    rng = np.random.default_rng(2)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 5, rng)
+    rs = rng.integers(1, 2 ** 31 - 2, 5 * 7).astype(np.uint32)
+    got = solver.solve_islands(None, seeds, 7, 10, rng_seeds=rs)
+    ref = oracle_lib.oracle_solve_islands(oracle, rm, pr, oracle_lib.make_cfg(population=32), None, seeds, 7, 10, rng_seeds=rs)
+    for k in ("solutions", "fitness", "success", "island", "steps"):
+        assert np.array_equal(got[k], ref[k]), k

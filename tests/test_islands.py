@@ -1,0 +1,142 @@
+"""many differently seeded islands per query, reduced like IKParallel::solve reduces its
+threads (src/ik_parallel.h:218-258), then the plugin's angle wrap (src/kinematics_plugin.cpp:580-611).
+CPU part: the oracle's restatement against an independent numpy statement and against the simulated kernel."""
+import math
+
+import numpy as np
+import pytest
+
+import hostsim_lib
+import oracle_lib
+from bio_ik_b200 import goals as G, robots, workloads
+from bio_ik_b200.problem import Problem
+
+
+@pytest.fixture(scope="module")
+def sim():
+    return hostsim_lib.HostSim()
+
+
+def numpy_wrap(v, r, lo, hi):
+    """kinematics_plugin.cpp:586-610, one variable"""
+    if r < v - math.pi or r > v + math.pi:
+        v -= r
+        v /= 2 * math.pi
+        v += 0.5
+        v -= math.floor(v)
+        v -= 0.5
+        v *= 2 * math.pi
+        v += r
+    if v > hi:
+        v -= math.ceil(max(0.0, v - hi) / (2 * math.pi)) * (2 * math.pi)
+    if v < lo:
+        v += math.ceil(max(0.0, lo - v) / (2 * math.pi)) * (2 * math.pi)
+    return min(max(v, lo), hi)
+
+
+def fake_runs(rng, robot, problem, Q, islands, success_rate):
+    B = Q * islands
+    runs = dict(solutions=rng.uniform(-12, 12, (B, robot.n_vars)), fitness=rng.uniform(0, 1, B), success=(rng.uniform(0, 1, B) < success_rate).astype(np.int32),
+                steps=rng.integers(1, 30, B).astype(np.int32))
+    runs["fitness"][rng.integers(0, B, B // 4)] = 0.25  # ties: the first island must win
+    return runs
+
+
+@pytest.mark.parametrize("secondary", [False, True])
+def test_selection_and_wrap_against_numpy(oracle, sim, secondary):
+    rm, groups = robots.pr2_like()
+    g = groups["right_arm"]
+    gl = [G.PoseGoal("r_wrist_roll_link")] + ([G.MinimalDisplacementGoal(1.0), G.AvoidJointLimitsGoal(0.5)] if secondary else [])
+    pr = Problem().initialize(rm, g, gl)
+    rng = np.random.default_rng(3)
+    Q, islands = 40, 6
+    seeds_q = workloads.sample_configurations(rm, pr.active_variables, Q, rng)
+    seeds = np.repeat(seeds_q, islands, axis=0)
+    gp = np.repeat(np.repeat(pr.default_goal_params()[None], Q, 0), islands, axis=0)
+    for rate in (0.0, 0.3, 1.0):
+        runs = fake_runs(rng, rm, pr, Q, islands, rate)
+        import ctypes as C
+        from bio_ik_b200 import _abi
+        res = dict(solutions=np.zeros((Q, rm.n_vars)), fitness=np.zeros(Q), success=np.zeros(Q, dtype=np.int32), island=np.zeros(Q, dtype=np.int32), steps=np.zeros(Q, dtype=np.int32))
+        r, p = rm.to_abi(), pr.to_abi()
+        oracle._check(oracle.lib.oracle_select_islands(C.byref(r), C.byref(p), Q, islands, _abi.dptr(gp), _abi.dptr(seeds), _abi.dptr(runs["solutions"]), _abi.dptr(runs["fitness"]), _abi.iptr(runs["success"]),
+                                                       _abi.iptr(runs["steps"]), 1, _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
+        # independent statement
+        act = pr.active_variables
+        sec = np.zeros(Q * islands)
+        if secondary:
+            _, s = oracle.approx_fitness(rm, pr, gp, seeds, seeds, runs["solutions"][:, act][:, None, :])
+            sec = s[:, 0]
+        lo, hi = rm.arrays["var_min"], rm.arrays["var_max"]
+        for q in range(Q):
+            sl = slice(q * islands, (q + 1) * islands)
+            f, ok = runs["fitness"][sl], runs["success"][sl]
+            if ok.any():
+                score = np.where(ok != 0, f + sec[sl], np.inf)
+                k = int(np.argmin(score))  # argmin returns the first minimum, like the strict '<' scan
+                best = score[k]
+            else:
+                k = int(np.argmin(f))
+                best = f[k]
+            assert res["island"][q] == k and res["fitness"][q] == best and res["success"][q] == ok[k] and res["steps"][q] == runs["steps"][sl][k]
+            want = runs["solutions"][q * islands + k].copy()
+            for iv in act:  # every active variable of the PR2-like arm is revolute and the robot has no mimic joints
+                want[iv] = numpy_wrap(want[iv], seeds_q[q, iv], lo[iv], hi[iv])
+            assert np.array_equal(res["solutions"][q], want)
+            for iv in act:
+                assert lo[iv] <= res["solutions"][q, iv] <= hi[iv]
+        # the simulated kernel gives the same bits
+        got = sim.select_islands(rm, pr, islands, gp, seeds, runs, wrap=True)
+        for k in res:
+            assert np.array_equal(got[k], res[k]), k
+        # without wrap the selected run comes back untouched
+        got = sim.select_islands(rm, pr, islands, gp, seeds, runs, wrap=False)
+        assert all(np.array_equal(got["solutions"][q], runs["solutions"][q * islands + res["island"][q]]) for q in range(Q))
+
+
+def test_wrap_properties():
+    """the wrapped angle is the same rotation (when no clamp was needed) and the closest copy to the seed inside the limits"""
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        lo, hi = sorted(rng.uniform(-7, 7, 2))
+        if hi - lo < 0.5:
+            continue
+        r = rng.uniform(lo, hi)
+        v = rng.uniform(-40, 40)
+        w = numpy_wrap(v, r, lo, hi)
+        assert lo <= w <= hi
+        if hi - lo >= 2 * math.pi + 1e-9:  # some copy of the angle always fits: no clamping
+            assert abs(math.remainder(w - v, 2 * math.pi)) < 1e-9
+
+
+def test_wrap_is_skipped_for_robots_with_mimic_joints_and_for_prismatic_variables(oracle, sim):
+    for maker, gname in ((robots.mimic_gripper_arm, None), (lambda: robots.random_tree(1), "all")):
+        rm, groups = maker()
+        g = groups[gname] if gname else groups[sorted(groups)[0]]
+        pr = Problem().initialize(rm, g, [G.PositionGoal(t) for t in g.tip_links])
+        rng = np.random.default_rng(1)
+        Q, islands = 8, 3
+        seeds = np.repeat(workloads.sample_configurations(rm, pr.active_variables, Q, rng), islands, axis=0)
+        runs = fake_runs(rng, rm, pr, Q, islands, 0.5)
+        got = sim.select_islands(rm, pr, islands, None, seeds, runs, wrap=True)
+        has_mimic = (rm.arrays["joint_mimic"] >= 0).any()
+        for q in range(Q):
+            src = runs["solutions"][q * islands + got["island"][q]]
+            for iv in range(rm.n_vars):
+                j = rm.getJointOfVariable(iv)
+                revolute = rm.links[j].joint_type == 1
+                if has_mimic or not revolute or iv not in pr.active_variables:
+                    assert got["solutions"][q, iv] == src[iv]
+
+
+def test_islands_oracle_end_to_end(oracle):
+    """more islands never hurt: the selected fitness is the best over the islands, success if any island succeeded"""
+    w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=6)
+    cfg = oracle_lib.make_cfg(population=18)
+    res = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, 4, 8, wrap=True)
+    runs = res["runs"]
+    for q in range(6):
+        sl = slice(4 * q, 4 * q + 4)
+        assert res["success"][q] == int(runs["success"][sl].any())
+        if not runs["success"][sl].any():
+            assert res["fitness"][q] == runs["fitness"][sl].min()
