@@ -276,7 +276,8 @@ __device__ __forceinline__ double fast_eval_one(const DProblem& P, int n, const 
 // T = tips, CH = children evaluated together per lane (register block),
 // GSPEC = 1: the problem is exactly one primary PoseGoal (the plugin's default goal for a one-tip group);
 // JOINT: joint-space goals present (accumulated in the gene loop)
-template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// NG: gene count as a compile-time constant (0 = P.n at run time): the gene loop unrolls, its pointer bumps fold into immediates
+template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;
@@ -286,7 +287,7 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
     if(S.done[q]) return;
-    const int n = P.n, C = S.C, G = P.G;
+    const int n = NG ? NG : P.n, C = S.C, G = P.G;
     const int R = mtab_row(C);
     const int nchunks = R / (32 * CH); // R is a power of two >= 32 * CH (select_evolve_fast)
 
@@ -455,6 +456,18 @@ template <int T, int CH, int GSPEC, bool JOINT> __global__ void __launch_bounds_
                 }
             };
             gene_step(std::true_type{}, 0, mA, mB);
+            if(NG)
+            {
+#pragma unroll
+                for(int i = 1; i < NG; i++)
+                {
+                    if(i & 1)
+                        gene_step(std::false_type{}, i, mB, mA);
+                    else
+                        gene_step(std::false_type{}, i, mA, mB);
+                }
+            }
+            else
             {
                 int i = 1;
 #pragma unroll 1
@@ -686,6 +699,8 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
     if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
 #define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
+    if(single_pose && cpl >= 3 && P.n == 7 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>;
+    if(single_pose && cpl >= 3 && P.n == 6 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>;
     if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
     switch(T)
     {
