@@ -138,10 +138,12 @@ def cpu_rate(args, w_small, seconds):
     o, kind = cpu_solver()
     cfg = oracle_lib.make_cfg(population=args.population)
     threads = usable_cpus()
-    n0 = min(len(w_small.seeds), max(64, 4 * threads))
-    t0 = time.perf_counter()
-    o.solve(w_small.robot, w_small.problem, cfg, w_small.goal_params[:n0], w_small.seeds[:n0], w_small.rng_seeds[:n0], args.solver_steps, nthreads=threads)
-    dt0 = time.perf_counter() - t0
+    n0 = min(len(w_small.seeds), max(64, 16 * threads))
+    dt0 = None
+    for _ in range(2):  # the first call builds the solver prototype and its lookup tables (set-up, not solving): calibrate on the second
+        t0 = time.perf_counter()
+        o.solve(w_small.robot, w_small.problem, cfg, w_small.goal_params[:n0], w_small.seeds[:n0], w_small.rng_seeds[:n0], args.solver_steps, nthreads=threads)
+        dt0 = time.perf_counter() - t0
     n1 = int(max(n0, seconds / max(dt0, 1e-6) * n0))
     reps = -(-n1 // len(w_small.seeds))
     gp, sd, rs = (np.concatenate([a] * reps)[:n1] for a in (w_small.goal_params, w_small.seeds, w_small.rng_seeds))
