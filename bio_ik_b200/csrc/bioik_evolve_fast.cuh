@@ -76,7 +76,8 @@ struct FastSmem
     __host__ __device__ int off_tip0() const { return off_pg() + 2 * n; }        // [T][8]
     __host__ __device__ int off_gp() const { return off_tip0() + 8 * T; }        // [G][12]
     __host__ __device__ int off_jrec() const { return off_gp() + 12 * G; }       // [n][4]  mid, halfspan, vel_weight, seed  (nj > 0)
-    __host__ __device__ int off_fit() const { return off_jrec() + (nj ? 4 * n : 0); } // [256] primary fitness per child slot
+    __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
+    __host__ __device__ int off_fit() const { return off_jq() + (nj ? 4 * FAST_MAX_JOINT_GOALS * n : 0); } // [256] primary fitness per child slot
     __host__ __device__ int off_sf() const { return off_fit() + 256; }                // [256] secondary fitness per child slot
     __host__ __device__ int total() const { return ((off_sf() + 256) + 1) & ~1; }
 };
@@ -291,21 +292,25 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
     const int R = mtab_row(C);
     const int nchunks = R / (32 * CH); // R is a power of two >= 32 * CH (select_evolve_fast)
 
-    int nj = 0, jg_goal[FAST_MAX_JOINT_GOALS], jg_type[FAST_MAX_JOINT_GOALS], jg_var[FAST_MAX_JOINT_GOALS];
+    // joint-space goals in goal order: slot j of the accumulators = the j-th of them; avoid_j = AvoidJointLimitsGoal
+    int nj = 0;
+    bool jq_avoid[FAST_MAX_JOINT_GOALS];
+#pragma unroll
+    for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++) jq_avoid[j] = false;
     if(JOINT)
         for(int g = 0; g < G; g++)
             if(is_joint_goal(P.goals[g].type) && nj < FAST_MAX_JOINT_GOALS)
             {
-                jg_goal[nj] = g;
-                jg_type[nj] = P.goals[g].type;
-                jg_var[nj] = P.goals[g].var_index;
+#pragma unroll
+                for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
+                    if(j == nj) jq_avoid[j] = P.goals[g].type == G_AVOID_JOINT_LIMITS;
                 nj++;
             }
 
     FastSmem L{n, T, G, JOINT ? 1 : 0};
     double* W = smem + (size_t)warp_in_block * L.total();
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
-    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
+    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
 
     // ---- stage the task -------------------------------------------------------------------
@@ -335,6 +340,36 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
     }
     for(int k = lane; k < G * GOAL_NPARAM; k += 32) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
     __syncwarp();
+    if(JOINT)
+    {
+        // One record per (joint-space goal, gene): every such goal adds ((x - centre) [-> max(0, |.| * 2 - half span)]) * weight,
+        // squared, for the genes it applies to (goal_types.h:387-465,494-498).  RegularizationGoal and JointVariableGoal have
+        // no weight factor: * 1.0 is exact; JointVariableGoal's (p0 - x)^2 == (x - p0)^2 bit for bit and 0.0 + that == that.
+        int j = 0;
+        for(int g = 0; g < G; g++)
+        {
+            const DGoal& gl = P.goals[g];
+            if(!is_joint_goal(gl.type) || j >= FAST_MAX_JOINT_GOALS) continue;
+            for(int i = lane; i < n; i += 32)
+            {
+                const DGene& Gn = P.genes[i];
+                double c = 0.0, w = 1.0, on = 1.0;
+                const double mid = (Gn.vmin + Gn.vmax) * 0.5, seedv = seed[Gn.var];
+                switch(gl.type)
+                {
+                case G_AVOID_JOINT_LIMITS: c = mid, w = Gn.vel_weight, on = Gn.clip_max != DBLMAX ? 1.0 : 0.0; break;
+                case G_CENTER_JOINTS: c = mid, w = Gn.vel_weight, on = Gn.clip_max != DBLMAX ? 1.0 : 0.0; break;
+                case G_REGULARIZATION: c = seedv; break;
+                case G_MINIMAL_DISPLACEMENT: c = seedv, w = Gn.vel_weight; break;
+                default: c = s_gp[g * GOAL_NPARAM], on = gl.var_index == i ? 1.0 : 0.0; break; // G_JOINT_VARIABLE
+                }
+                double* r = s_jq + ((size_t)j * n + i) * 4;
+                r[0] = c, r[1] = Gn.span * 0.5, r[2] = w, r[3] = on;
+            }
+            j++;
+        }
+        __syncwarp();
+    }
 
     // Fitness of the two parents under this step's approximator.  Within a step the parents of generation
     // g+1 are the winners of generation g, whose fitness (same genes, same operations) is already known,
@@ -444,14 +479,23 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
                 dp += 8;
                 if(JOINT)
                 {
-                    const double mid = s_jrec[4 * i + 0], halfspan = s_jrec[4 * i + 1], vw = s_jrec[4 * i + 2], seedv = s_jrec[4 * i + 3];
 #pragma unroll
                     for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
                         if(j < nj)
                         {
-                            const double p0 = s_gp[jg_goal[j] * GOAL_NPARAM];
+                            const double* r = s_jq + ((size_t)j * n + i) * 4;
+                            if(r[3] != 0.0) // warp-uniform: the goal applies to this gene
+                            {
+                                const double c = r[0], hs = r[1], w = r[2];
 #pragma unroll
-                            for(int k = 0; k < CH; k++) joint_goal_accumulate(jg_type[j], jg_var[j], i, x[k], hi, mid, halfspan, vw, seedv, p0, acc[k][j]);
+                                for(int k = 0; k < CH; k++)
+                                {
+                                    double dd = x[k] - c;
+                                    if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
+                                    dd *= w;
+                                    acc[k][j] += dd * dd;
+                                }
+                            }
                         }
                 }
             };
@@ -698,6 +742,7 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);
     int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
     if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
+    if(J && cpl > 2) cpl = 2;      // joint-space accumulators on top of the frame accumulators: blocks of 4 spill (cfg4: 29.5 vs 21.8 ms per pass)
 #define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
     if(single_pose && cpl >= 3 && P.n == 7 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>;
     if(single_pose && cpl >= 3 && P.n == 6 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>;
