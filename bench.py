@@ -338,7 +338,7 @@ def main():
                 "note": "persistent per-task state lives in shared memory/L2, so HBM traffic is tiny by design; the binding unit is the FP64 pipe"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the contract asks for it on rank 0 at N=1 only
         wcpu, _ = make_workload(args, None)
         nb = B
         wcpu.goal_params, wcpu.seeds, wcpu.rng_seeds = batches[0][0][:nb], batches[0][1][:nb], batches[0][2][:nb]
