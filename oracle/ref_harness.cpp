@@ -39,6 +39,31 @@
 #include <emmintrin.h>
 #include <immintrin.h>
 #include <x86intrin.h>
+#include "bioik_oracle.hpp" // only for det_sincos / det_acos (the arithmetic contract's sin, cos, acos)
+
+// Test switch: with ref_set_contract_math(1) the two unqualified calls cos(half_angle) / sin(half_angle) of the
+// reference's getJointFrame (forward_kinematics.h:103-104) resolve to these functions instead of libm's, and ConeGoal's
+// acos goes through the shim hook - the reference then computes with the arithmetic contract of DESIGN.md §3 and can be
+// compared with the CUDA path directly, bit for bit.  Default (0): libm, i.e. the reference exactly as it is.
+namespace bio_ik
+{
+static int g_contract_math = 0;
+inline double sin(double x)
+{
+    if(!g_contract_math) return ::sin(x);
+    double s, c;
+    bioik_oracle::det_sincos(x, &s, &c);
+    return s;
+}
+inline double cos(double x)
+{
+    if(!g_contract_math) return ::cos(x);
+    double s, c;
+    bioik_oracle::det_sincos(x, &s, &c);
+    return c;
+}
+}
+
 #include "ik_evolution_2.cpp"
 #include "problem.cpp"
 
@@ -291,6 +316,13 @@ template <int M> void traceOut(IKSolver* s, size_t n, int b, double* out_genes, 
 extern "C" {
 
 const char* ref_last_error() { return g_error.c_str(); }
+
+// 1: sin / cos / acos of the arithmetic contract (det_sincos, det_acos) inside the reference's code; 0: libm (default)
+void ref_set_contract_math(int on)
+{
+    bio_ik::g_contract_math = on;
+    tf2::vector3AngleAcosHook() = on ? &bioik_oracle::det_acos : nullptr;
+}
 
 // Same signature as oracle_solve_batch (tables argument unused: the reference owns its static tables).
 int ref_solve_batch(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, void*, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit, int, int nthreads,

@@ -11,6 +11,13 @@ inline tf2Scalar tf2Acos(tf2Scalar x)
     if(x > tf2Scalar(1)) x = tf2Scalar(1);
     return std::acos(x);
 }
+// test hook (ref_harness.cpp): replaces the acos of Vector3::angle - ConeGoal's only transcendental (goal_types.h:706) -
+// by the arithmetic contract's det_acos, so the reference's code can be compared with the GPU path bit for bit
+inline double (*&vector3AngleAcosHook())(double)
+{
+    static double (*hook)(double) = nullptr;
+    return hook;
+}
 class Vector3
 {
 public:
@@ -40,6 +47,13 @@ public:
     tf2Scalar angle(const Vector3& v) const
     {
         tf2Scalar s = tf2Sqrt(length2() * v.length2());
+        if(auto hook = vector3AngleAcosHook())
+        {
+            tf2Scalar c = dot(v) / s;
+            if(c < tf2Scalar(-1)) c = tf2Scalar(-1);
+            if(c > tf2Scalar(1)) c = tf2Scalar(1);
+            return hook(c);
+        }
         return tf2Acos(dot(v) / s);
     }
     Vector3 cross(const Vector3& v) const

@@ -198,6 +198,7 @@ class Reference:
         lib.ref_approx_fitness_batch.argtypes = [RP, PP, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp]
         lib.ref_effective_goal_params.argtypes = [RP, PP, C.c_int, dp, dp]
         lib.ref_effective_link_origins.argtypes = [RP, dp]
+        lib.ref_set_contract_math.argtypes = [C.c_int]
         lib.ref_table.argtypes = [C.c_int, C.c_uint32]
         lib.ref_table.restype = dp
 
@@ -208,6 +209,11 @@ class Reference:
     def _gp(self, problem, goal_params, B):
         gp = np.repeat(problem.default_goal_params()[None], B, 0) if goal_params is None else goal_params
         return np.ascontiguousarray(gp, dtype=np.float64).reshape(B, problem.n_goals, _abi.GOAL_NPARAM)
+
+    def contract_math(self, on):
+        """True: the reference's sin / cos (forward_kinematics.h:103-104) and ConeGoal's acos use the arithmetic contract's
+        det_sincos / det_acos instead of libm; everything else of the reference runs unchanged"""
+        self.lib.ref_set_contract_math(int(bool(on)))
 
     def table(self, which, seed, n=1 << 23):
         return np.ctypeslib.as_array(self.lib.ref_table(which, seed), shape=(1 << 23,))[:n].copy()

@@ -326,3 +326,33 @@ def test_solve_islands_default_goal_parameters_and_seeds(oracle):
     ref = oracle_lib.oracle_solve_islands(oracle, rm, pr, oracle_lib.make_cfg(population=32), None, seeds, 7, 10, rng_seeds=rs)
     for k in ("solutions", "fitness", "success", "island", "steps"):
         assert np.array_equal(got[k], ref[k]), k
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA path against the REFERENCE'S OWN CODE (oracle/_ref, prebuilt where /root/reference exists; travels to the GPU box)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,pop,steps", [("cfg2", 256, 128, 25), ("cfg2", 64, 18, 25), ("cfg1", 1, 64, 25), ("cfg4", 16, 128, 10)])
+def test_gpu_equals_the_reference_code_with_contract_math(name, B, pop, steps):
+    """No oracle in between: the reference's src/ik_evolution_2.cpp + src/problem.cpp + forward_kinematics.h, compiled in place
+    (oracle/ref_harness.cpp), with its two libm calls sin / cos swapped for the arithmetic contract's det_sincos and its child pool
+    re-sized to `pop` - against bioik_solve_batch on the GPU.  Bit-identical joint angles, fitness, success flags and every
+    species' genes and gradients (single-tip problems: quirk Q2 does not apply)."""
+    try:
+        ref = oracle_lib.Reference("strict")
+    except (FileNotFoundError, OSError) as e:
+        pytest.skip(f"reference build not available here: {e}")
+    w = workloads.make(name, lambda rm, pr, v: oracle_lib.Oracle().fk(rm, pr, v), batch=B)
+    B = len(w.rng_seeds)
+    # the numbers the reference stores after its own normalising constructors / Isometry3d conversion (ulp-level changes)
+    robot, gp = ref.effective_robot(w.robot), ref.effective_goal_params(w.robot, w.problem, w.goal_params, B)
+    solver = IKSolver(robot, mode="bio2_memetic", population=pop, random_seed=1, device=0).initialize(w.problem)
+    got = solver.trace(gp, w.seeds, w.rng_seeds, steps)
+    res = solver.solve_batch(gp, w.seeds, w.rng_seeds, steps)
+    ref.contract_math(True)
+    try:
+        want = ref.solve(w.robot, w.problem, oracle_lib.make_cfg(population=pop), w.goal_params, w.seeds, w.rng_seeds, steps)
+    finally:
+        ref.contract_math(False)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(res["success"], want["success"]) and np.array_equal(res["solutions"], want["solutions"])

@@ -184,6 +184,38 @@ def test_cone_goal_is_the_one_exception(ref, oracle):
     assert np.allclose(prim, b["primary"], rtol=1e-13, atol=0)
 
 
+def test_reference_with_contract_math_equals_the_default_oracle(ref, oracle):
+    """The other direction: instead of giving the oracle libm, give the REFERENCE the contract's sin / cos / acos
+    (ref_harness.cpp: the two unqualified calls of forward_kinematics.h:103-104 resolve to bio_ik::sin / cos; ConeGoal's
+    acos through a shim hook).  The reference's code then equals the oracle in its default - product - arithmetic,
+    ConeGoal included, which is what the GPU path is tested against."""
+    ref.contract_math(True)
+    try:
+        for name, B, pop in (("cfg2", 48, 128), ("cfg2", 32, 18), ("cfg4", 8, 64)):
+            w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+            cfg = oracle_lib.make_cfg(population=pop)
+            gpe = ref.effective_goal_params(w.robot, w.problem, w.goal_params, B)
+            a = oracle.solve(ref.effective_robot(w.robot), w.problem, cfg, gpe, w.seeds, w.rng_seeds, 25)  # default flags: the arithmetic contract
+            b = ref.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 25)
+            for k in KEYS:
+                assert np.array_equal(a[k], b[k]), (name, k)
+        # ConeGoal, now to the bit
+        rm, groups = robots.pr2_like()
+        g = groups["all"]
+        gl = [G.ConeGoal("r_wrist_roll_link", (1, 0, 0), (0, 0.6, 0.8), 0.3, weight=0.5, position=(0.5, 0, 1), position_weight=0.7), G.ConeGoal("l_wrist_roll_link", (0, 0, 1), (1, 0, 0), 1.2)]
+        pr = Problem().initialize(rm, g, gl)
+        rng = np.random.default_rng(5)
+        B, M, n = 16, 8, len(pr.active_variables)
+        base = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+        genes = base[:, pr.active_variables][:, None, :] + rng.normal(0, 0.2, (B, M, n))
+        gp = np.repeat(pr.default_goal_params()[None], B, 0)
+        b = ref.approx_fitness(rm, pr, gp, base, base, genes)
+        prim, _ = oracle.approx_fitness(ref.effective_robot(rm), pr, ref.effective_goal_params(rm, pr, gp, B), base, base, genes)
+        assert np.array_equal(prim, b["primary"])
+    finally:
+        ref.contract_math(False)
+
+
 def test_mimic_joints_and_prismatic(ref, oracle):
     """updateMimic, the mimic branches of the Jacobian and prismatic joints (forward_kinematics.h:640-760) in the reference's code"""
     rm, groups = robots.mimic_gripper_arm()
