@@ -87,6 +87,8 @@ struct bioik_ctx
     double *d_q_gp = nullptr, *d_q_seeds = nullptr, *d_q_sol = nullptr, *d_q_fit = nullptr;
     int32_t *d_q_succ = nullptr, *d_q_island = nullptr, *d_q_steps = nullptr;
     int queryQ = 0;
+    int32_t* d_flag = nullptr; // "any run still active" (bioik_solve_islands polls it between bursts)
+    int32_t* h_flag = nullptr; // pinned host copy
     bool serial_split = false; // BIOIK_SERIAL_SPLIT=1: one launch per phase of the serial kernel (phase timing study)
     double ms_phase[3] = {0, 0, 0};
 };
@@ -137,6 +139,7 @@ int ensure_state(bioik_ctx* ctx, int B)
         (size_t)B * 2 * n * 8,         // base
         (size_t)B * 2 * T * 7 * 8,     // tip0
         (size_t)B * 2 * T * n * 7 * 8, // delta
+        (size_t)B * 4,                 // qstep
     };
     size_t total = 0;
     for(size_t s : sizes) total += align_up(s);
@@ -162,6 +165,7 @@ int ensure_state(bioik_ctx* ctx, int B)
     S.base = (double*)take(sizes[11]);
     S.tip0 = (double*)take(sizes[12]);
     S.delta = (double*)take(sizes[13]);
+    S.qstep = (int32_t*)take(sizes[14]);
     ctx->capB = B;
     return BIOIK_OK;
 }
@@ -300,11 +304,13 @@ DState slice_state(const DState& S, const DProblem& P, int q0, int nq)
     H.base += q * 2 * n;
     H.tip0 += q * 2 * T * 7;
     H.delta += q * 2 * T * n * 7;
+    H.qstep += q; // only meaningful without islands (enqueue_solve does not slice island batches)
     return H;
 }
 
 // enqueue a whole solve on `st`; all pointers are device pointers
-int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
+int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps,
+                  int islands = 0, bool poll = false)
 {
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
     if(B <= 0 || steps < 0 || !d_seeds || !d_rs) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
@@ -321,6 +327,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     S.memetic_iters = ctx->cfg.memetic_iters;
     S.total_steps = steps;
     S.early_exit = early_exit;
+    S.islands = islands;
     if(!d_gp)
     {
         // no per-query parameters: broadcast the defaults of BioikGoal::p
@@ -364,7 +371,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         // Production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial.
         // The batch is cut in two halves that ping-pong between two internal streams, so the latency-bound serial
         // kernel of one half runs in the shadow of the throughput-bound generation kernel of the other half.
-        const int H = (B >= 2048 && ctx->pipeline) ? 2 : 1;
+        const int H = (B >= 2048 && ctx->pipeline && islands <= 1) ? 2 : 1;
         int q0[3] = {0, H == 2 ? (B / 2) : B, B};
         DState Sh[2];
         for(int h = 0; h < H; h++) Sh[h] = slice_state(S, P, q0[h], q0[h + 1] - q0[h]);
@@ -445,6 +452,17 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
                 if(H == 2) cudaStreamWaitEvent(ss, ctx->ev_evolve[h], 0);
                 const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
                 if((rc = launch_serial(h, step, phases)) != BIOIK_OK) return rc;
+                if(poll && H == 1 && (step + 1) % 4 == 0 && step + 1 < steps)
+                {
+                    // latency mode: after each of the driver's 4-step bursts ask the device whether any run is still going
+                    // and stop enqueueing when none is (every kernel would return at once, but 2 launches per step add up)
+                    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, 4, st));
+                    k_any_active<<<(B + 255) / 256, 256, 0, st>>>(S, step + 1, ctx->d_flag);
+                    if((rc = check_launch(ctx, "k_any_active")) != BIOIK_OK) return rc;
+                    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, st));
+                    CU(ctx, cudaStreamSynchronize(st));
+                    if(*ctx->h_flag == 0) step = steps; // leave both loops
+                }
             }
         if(H == 2)
         {
@@ -459,7 +477,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     for(int step = 0; step < steps; step++)
     {
         Timed t1(ctx, st, 1);
-        k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S);
+        k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
         if((rc = check_launch(ctx, "k_prepare")) != BIOIK_OK) return rc;
         t1.done();
         Timed t2(ctx, st, 0);
@@ -587,6 +605,8 @@ void bioik_destroy(bioik_ctx* ctx)
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
+    cudaFree(ctx->d_flag);
+    if(ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
     if(ctx->stream_evolve) cudaStreamDestroy(ctx->stream_evolve);
@@ -739,7 +759,12 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
     }
     if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr; // the staging buffers are shared with the cached solve_batch graph
     ctx->graph_B = -1;
-    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+    if(!ctx->d_flag)
+    {
+        CU(ctx, cudaMalloc(&ctx->d_flag, 4));
+        CU(ctx, cudaMallocHost(&ctx->h_flag, 4));
+    }
+    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps, islands, early_exit != 0);
     if(rc != BIOIK_OK) return rc;
     // without per-query parameters enqueue_solve has broadcast the defaults into d_gp
     k_select_islands<<<(Q + 127) / 128, 128, 0, st>>>(ctx->dP, Q, islands, ctx->d_gp, ctx->d_seeds, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps, wrap, ctx->d_q_sol, ctx->d_q_fit, ctx->d_q_succ, ctx->d_q_island,

@@ -287,7 +287,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
     const int task = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
-    if(S.done[q]) return;
+    if(run_done(S, q, step)) return;
     const int n = NG ? NG : P.n, C = S.C, G = P.G;
     const int R = mtab_row(C);
     const int nchunks = R / (32 * CH); // R is a power of two >= 32 * CH (select_evolve_fast)

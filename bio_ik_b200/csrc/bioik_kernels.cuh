@@ -20,7 +20,7 @@ namespace bioik
 // field ("array of per-query records"), fields in separate arrays.
 struct DState
 {
-    int32_t B, C, gens, memetic, memetic_iters, total_steps, early_exit, pad;
+    int32_t B, C, gens, memetic, memetic_iters, total_steps, early_exit, islands; // islands > 1: run q is island q % islands of query q / islands
     // inputs
     const double* goal_params; // [B][G][NPARAM]
     const double* seeds;       // [B][n_vars]
@@ -37,6 +37,7 @@ struct DState
     int32_t* steps;    // [B] step() calls executed
     int32_t* success;  // [B]
     int32_t* ccount;   // [B][2][gens] pre-selection child_count (only with secondary goals)
+    int32_t* qstep;    // [B / islands] step count at which the first island of the query passed the success test (INT32_MAX: none yet)
     // approximator of the current step
     double* base;  // [B][2][n]
     double* tip0;  // [B][2][T][7]
@@ -47,6 +48,18 @@ struct DState
     const int32_t* gauss_off;  // [total_steps*2*gens] slab start of each reproduce() call
     const uint8_t* rate_exp;   // [total_steps*2*gens][C-2] fast_random_index(16) per child
 };
+
+// A run is over when its own early exit fired, or - early_exit == 2, the islands of one query - when a sibling island passed
+// the driver's success test at an EARLIER check: IKParallel's `finished` flag (src/ik_parallel.h:160,164,171,180), which
+// makes every other solver thread leave its loop at the next test.  `step` = index of the step() about to run; a success
+// found during launch `step` records qstep = step + 1, so runs of the same launch never see it (deterministic).
+__device__ __forceinline__ bool run_done(const DState& S, int q, int step) { return S.done[q] || (S.early_exit == 2 && S.islands > 1 && S.qstep[q / S.islands] <= step); }
+__device__ __forceinline__ void note_success(const DState& S, int q, int steps_done)
+{
+    if(!S.early_exit) return;
+    S.done[q] = 1;
+    if(S.early_exit == 2 && S.islands > 1) atomicMin(&S.qstep[q / S.islands], steps_done);
+}
 
 constexpr uint32_t RANDOM_BUFFER_MASK = (1u << 23) - 1;
 constexpr uint32_t UNIFORM_INDEX0 = 6165936u; // XORShift64 output #1 & mask (src/ik_base.h:122)
@@ -102,6 +115,7 @@ __global__ void k_init(const DProblem* __restrict__ Pp, DState S)
     draw_preselect_counts(P, S, q, r);
     S.rng[q] = r;
     S.done[q] = 0;
+    S.qstep[q] = 0x7fffffff;
     S.steps[q] = 0;
     S.success[q] = 0;
 }
@@ -109,13 +123,13 @@ __global__ void k_init(const DProblem* __restrict__ Pp, DState S)
 // ---------------------------------------------------------------------------
 // src/ik_evolution_2.cpp:341-346: applyConfiguration + initializeMutationApproximator
 // ---------------------------------------------------------------------------
-__global__ void k_prepare(const DProblem* __restrict__ Pp, DState S)
+__global__ void k_prepare(const DProblem* __restrict__ Pp, DState S, int step)
 {
     const DProblem& P = *Pp;
     int task = blockIdx.x * blockDim.x + threadIdx.x;
     if(task >= S.B * 2) return;
     int q = task >> 1;
-    if(S.done[q]) return;
+    if(run_done(S, q, step)) return;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
     const double* genes = S.genes + ((size_t)task * 2 + 0) * P.n;
     double vars[MAX_VARS], frames[MAX_SLOTS * 7];
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(128) k_evolve(const DProblem* __restrict__ Pp,
     const int task = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
-    if(S.done[q]) return;
+    if(run_done(S, q, step)) return;
     const int n = P.n, T = P.T, C = S.C;
     EvolveSmem L{n, T, P.G};
     double* W = smem + (size_t)warp_in_block * L.total();
@@ -357,7 +371,7 @@ __global__ void k_memetic(const DProblem* __restrict__ Pp, DState S, int step)
     int task = blockIdx.x * blockDim.x + threadIdx.x;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
-    if(S.done[q]) return;
+    if(run_done(S, q, step)) return;
     const int n = P.n, T = P.T;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
     const double* gp = S.goal_params + (size_t)q * P.G * GOAL_NPARAM;
@@ -453,7 +467,7 @@ __global__ void k_species(const DProblem* __restrict__ Pp, DState S, int step)
     const DProblem& P = *Pp;
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if(q >= S.B) return;
-    if(S.done[q]) return;
+    if(run_done(S, q, step)) return;
     const int n = P.n;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
     const double* gp = S.goal_params + (size_t)q * P.G * GOAL_NPARAM;
@@ -509,7 +523,7 @@ __global__ void k_species(const DProblem* __restrict__ Pp, DState S, int step)
         exact_primary_fitness(P, seed, gp, sol, tips);
         int ok = check_solution(P, gp, tips, sol, seed) ? 1 : 0;
         S.success[q] = ok;
-        if(ok && S.early_exit) S.done[q] = 1;
+        if(ok) note_success(S, q, steps);
     }
     draw_preselect_counts(P, S, q, rng); // random_index draws of the NEXT step's generations (:369)
     S.rng[q] = rng;
@@ -541,6 +555,13 @@ __global__ void k_finalize(const DProblem* __restrict__ Pp, DState S, double* ou
 // Many differently seeded islands of ONE query: the batch holds Q x islands runs,
 // run q * islands + k being island k of query q.
 // ---------------------------------------------------------------------------
+// host polling between 4-step bursts: *flag = 1 if any run would still execute step `step`
+__global__ void k_any_active(DState S, int step, int32_t* flag)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q < S.B && !run_done(S, q, step)) *flag = 1;
+}
+
 // island inputs from query inputs: goal parameters [Q][G][NPARAM] and seeds [Q][n_vars] repeated `islands` times
 __global__ void k_expand_islands(int Q, int islands, int per_gp, int per_seed, const double* gp, const double* seeds, double* gp_out, double* seeds_out)
 {

@@ -63,7 +63,7 @@ template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PR
     const bool valid = task_raw < 2 * S.B;
     const int task = valid ? task_raw : 2 * S.B - 1;
     const int q = task >> 1, slot = task & 1;
-    bool alive = valid && !S.done[q] && S.memetic;
+    bool alive = valid && !run_done(S, q, step) && S.memetic;
     const int n = P.n, T = P.T, G = P.G, T7 = 7 * P.T;
 
     const GroupLayout L{n, T, G, W};
@@ -218,7 +218,7 @@ template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PR
     }
 
     // individuals[0].genes back to the state (gradients are not touched by the memetic step)
-    if(valid && !S.done[q] && S.memetic)
+    if(valid && !run_done(S, q, step) && S.memetic)
     {
         double* og0 = S.genes + ((size_t)task * 2 + 0) * n;
         for(int i = gl; i < n; i += W) og0[i] = ind[i];

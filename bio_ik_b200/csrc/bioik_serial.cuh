@@ -224,7 +224,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
     const bool valid = task_raw < 2 * S.B;
     const int task = valid ? task_raw : 2 * S.B - 1;
     const int q = task >> 1, slot = task & 1;
-    const bool active = valid && !S.done[q];
+    const bool active = valid && !run_done(S, q, step);
     const int n = P.n, T = P.T, G = P.G;
 
     // ---- per-thread columns --------------------------------------------------------------------
@@ -554,7 +554,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
                     }
                     const int ok = check_solution(P, cgp, CSC(ts), CSC(xs), seed) ? 1 : 0;
                     S.success[q] = ok;
-                    if(ok && S.early_exit) S.done[q] = 1;
+                    if(ok) note_success(S, q, steps);
                 }
             }
             // write the species back (to its new slot)

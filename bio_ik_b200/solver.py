@@ -77,11 +77,13 @@ class IKSolver:
                                                _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["steps"])))
         return res
 
-    def solve_islands(self, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=False, wrap=True):
+    def solve_islands(self, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=2, wrap=True):
         """Q MoveIt-style queries, each solved by `islands` differently seeded runs in one batch and reduced like
         IKParallel::solve reduces its threads (src/ik_parallel.h:218-258: best successful island by primary +
         secondary fitness, else best primary fitness); wrap=True applies the plugin's angle wrap towards the seed
-        (src/kinematics_plugin.cpp:580-611).  rng_seeds: [Q * islands] (default 1 + run index)."""
+        (src/kinematics_plugin.cpp:580-611).  rng_seeds: [Q * islands] (default 1 + run index).
+        early_exit: 0 = every island runs `steps` steps, 1 = an island stops at its own success, 2 = all islands of a query stop
+        after the check at which the first of them succeeded (the reference driver's `finished` flag, src/ik_parallel.h:160-186)."""
         rm, pr = self.robot_model, self.problem
         seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, rm.n_vars)
         Q = seeds.shape[0]

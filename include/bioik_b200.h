@@ -210,6 +210,10 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
  *   - selection = IKParallel::solve (src/ik_parallel.h:218-258): among the successful islands the smallest
  *     primary (+ secondary, when the problem has secondary goals) fitness, else the smallest primary fitness;
  *     first island wins ties;
+ *   - early_exit: 0 = every island runs `steps` steps; 1 = an island stops at its own first successful test; 2 = like
+ *     the reference's driver, whose `finished` flag makes every solver thread leave its loop once one of them has
+ *     passed the test (src/ik_parallel.h:160-186): all islands of a query stop after the 4-step check at which the
+ *     first of them succeeded (deterministic: the islands run in lock step);
  *   - wrap != 0 applies the plugin's angle wrap to the selected solution (src/kinematics_plugin.cpp:580-611):
  *     revolute variables of robots without mimic joints are moved by multiples of 2 pi next to the seed, wrapped
  *     inside [min, max] and clamped.  (MoveIt's enforcePositionBounds, :614, is MoveIt code and not applied.)

@@ -45,6 +45,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -1551,6 +1552,57 @@ inline size_t selectBestResult(Problem& problem, const std::vector<std::vector<d
                 best_index = i;
             }
     return best_index;
+}
+
+// src/ik_parallel.h:148-190 with the wall-clock timeout replaced by a step budget: `islands` solvers of one problem run in
+// lock step (the reference's threads run freely; lock step is the deterministic reading of the same loop).  After every
+// burst of 4 steps each solver records its solution, success flag and fitness (:173-181); query_exit = the `finished` flag
+// (:160,180): once any solver has succeeded nobody starts another burst.  island_exit = a solver that succeeded stops by
+// itself (the batch contract's per-run early exit).
+struct IslandRuns
+{
+    std::vector<std::vector<double>> solutions;
+    std::vector<double> fitness;
+    std::vector<int> success, steps;
+};
+inline IslandRuns solveIslands(const RobotModel& robot, const Tables& tables, const Problem& problem, const uint32_t* rng_seeds, size_t islands, const SolverConfig& cfg, int steps, bool island_exit, bool query_exit,
+                               Options opt = Options())
+{
+    std::vector<std::unique_ptr<IKEvolution2>> solvers;
+    for(size_t i = 0; i < islands; i++)
+    {
+        solvers.emplace_back(new IKEvolution2(&robot, tables, rng_seeds[i], cfg, opt));
+        solvers.back()->initialize(problem);
+    }
+    IslandRuns r;
+    r.solutions.resize(islands), r.fitness.assign(islands, 0.0), r.success.assign(islands, 0), r.steps.assign(islands, 0);
+    std::vector<int> stopped(islands, 0);
+    int done = 0;
+    bool finished = false;
+    while(done < steps && !finished)
+    {
+        int burst = std::min(4, steps - done);
+        for(size_t i = 0; i < islands; i++)
+        {
+            if(stopped[i]) continue;
+            for(int k = 0; k < burst; k++) solvers[i]->step();
+            r.steps[i] = done + burst;
+            std::vector<double> result = solvers[i]->getSolution();
+            solvers[i]->model.applyConfiguration(result);
+            bool ok = solvers[i]->checkSolution(result, solvers[i]->model.getTipFrames());
+            if(ok && (island_exit || query_exit)) stopped[i] = 1;
+            if(ok && query_exit) finished = true;
+        }
+        done += burst;
+    }
+    for(size_t i = 0; i < islands; i++)
+    {
+        r.solutions[i] = solvers[i]->getSolution();
+        solvers[i]->model.applyConfiguration(r.solutions[i]);
+        r.success[i] = solvers[i]->checkSolution(r.solutions[i], solvers[i]->model.getTipFrames());
+        r.fitness[i] = solvers[i]->computeFitness(r.solutions[i], solvers[i]->model.getTipFrames());
+    }
+    return r;
 }
 
 // src/kinematics_plugin.cpp:580-611 — angle wrap of the returned state (in place)

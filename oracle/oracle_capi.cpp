@@ -437,5 +437,68 @@ int oracle_select_islands(const BioikRobot* robot, const BioikProblem* problem, 
     }
 }
 
+// The whole of bioik_solve_islands on the CPU: lock-step islands (solveIslands), IKParallel's selection, the plugin's wrap.
+// early_exit: 0 none, 1 per island, 2 per query (the reference's `finished` flag).  goal_params [Q][G][NPARAM] or NULL, seeds [Q][n_vars],
+// rng_seeds [Q * islands].  Optional per-run outputs run_* [Q * islands]...
+int oracle_solve_islands(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, void* tables, int Q, int islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps,
+                         int early_exit, int wrap, int flags, int nthreads, double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps, double* run_solutions, double* run_fitness,
+                         int32_t* run_success, int32_t* run_steps)
+{
+    try
+    {
+        RobotModel rm = makeRobot(robot);
+        Problem pr0 = makeProblem(rm, problem);
+        SolverConfig sc = makeCfg(cfg);
+        Options opt;
+        opt.libm_sincos = (flags & 1) != 0;
+        opt.fma_approx = (flags & 2) == 0;
+        opt.fma_approx1 = (flags & 4) == 0;
+        opt.stale_tips = (flags & 8) != 0;
+        const Tables& tb = *(const Tables*)tables;
+        std::atomic<int> failed(0);
+        std::string err;
+        parallelFor(Q, nthreads, [&](int q) {
+            try
+            {
+                Problem pr = pr0;
+                applyQuery(pr, problem, goal_params ? goal_params + (size_t)q * problem->n_goals * GOAL_NPARAM : nullptr, seeds + (size_t)q * rm.n_vars, rm.n_vars);
+                IslandRuns r = solveIslands(rm, tb, pr, rng_seeds + (size_t)q * islands, islands, sc, steps, early_exit == 1, early_exit == 2, opt);
+                double best;
+                size_t k = selectBestResult(pr, r.solutions, r.fitness, r.success, best);
+                std::vector<double> state = r.solutions[k];
+                if(wrap) wrapAngles(rm, pr, state);
+                std::copy(state.begin(), state.end(), out_solutions + (size_t)q * rm.n_vars);
+                if(out_fitness) out_fitness[q] = best;
+                if(out_success) out_success[q] = r.success[k];
+                if(out_island) out_island[q] = (int32_t)k;
+                if(out_steps) out_steps[q] = r.steps[k];
+                for(int i = 0; i < islands; i++)
+                {
+                    size_t b = (size_t)q * islands + i;
+                    if(run_solutions) std::copy(r.solutions[i].begin(), r.solutions[i].end(), run_solutions + b * rm.n_vars);
+                    if(run_fitness) run_fitness[b] = r.fitness[i];
+                    if(run_success) run_success[b] = r.success[i];
+                    if(run_steps) run_steps[b] = r.steps[i];
+                }
+            }
+            catch(std::exception& e)
+            {
+                if(!failed.exchange(1)) err = e.what();
+            }
+        });
+        if(failed)
+        {
+            g_error = err;
+            return 1;
+        }
+        return 0;
+    }
+    catch(std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 int oracle_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 }

@@ -20,9 +20,9 @@ for islands in (1, 16, 64, 256, 1024):
         for q in range(64):
             gp, sd = w.goal_params[q:q + 1], w.seeds[q:q + 1]
             if q < 4:
-                solver.solve_islands(gp, sd, islands, steps, early_exit=True)  # warm-up: sizes the state
+                solver.solve_islands(gp, sd, islands, steps, early_exit=2)  # warm-up: sizes the state
             t0 = time.perf_counter()
-            r = solver.solve_islands(gp, sd, islands, steps, early_exit=True)
+            r = solver.solve_islands(gp, sd, islands, steps, early_exit=2)
             lat.append(time.perf_counter() - t0)
             ok.append(int(r["success"][0]))
         lat = np.array(lat) * 1e3

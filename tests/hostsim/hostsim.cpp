@@ -68,6 +68,12 @@ static inline unsigned __ballot_sync(unsigned, bool pred)
     return acc;
 }
 static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
+static inline int atomicMin(int* a, int v)
+{
+    int old = *a;
+    if(v < old) *a = v;
+    return old;
+}
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline double __longlong_as_double(long long v)
 {
@@ -163,6 +169,10 @@ void hostsim_sincos(int n, const double* x, double* s, double* c)
     for(int i = 0; i < n; i++) d_sincos(x[i], s[i], c[i]);
 }
 
+// islands per query of the next hostsim_solve calls (0: plain batch), for early_exit == 2
+static int g_islands = 0;
+void hostsim_set_islands(int islands) { g_islands = islands; }
+
 // the launch sequence of enqueue_solve() in bioik_capi.cu, on host memory
 int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit, double* out_solutions,
                   double* out_fitness, int32_t* out_success, int32_t* out_steps, double* out_genes, double* out_gradients, double* out_species_fitness, int use_fast)
@@ -178,7 +188,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     make_schedules(std::max(steps, 1), cfg->generations, cfg->population, P.n, go, re);
     size_t n = P.n, T = P.T, gens = cfg->generations;
     std::vector<double> genes(B * 4 * n), grads(B * 4 * n), sfit(B * 2), sol(B * n), solfit(B), base(B * 2 * n), tip0(B * 2 * T * 7), delta(B * 2 * T * n * 7);
-    std::vector<int32_t> impr(B * 2), done(B), stp(B), succ(B), cc(B * 2 * gens);
+    std::vector<int32_t> impr(B * 2), done(B), stp(B), succ(B), cc(B * 2 * gens), qstep(B);
     std::vector<uint32_t> rng(B);
     std::vector<double> gp_default;
     if(!goal_params)
@@ -191,10 +201,10 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     }
     DState S;
     memset(&S, 0, sizeof(S));
-    S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit;
+    S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit, S.islands = g_islands;
     S.goal_params = goal_params, S.seeds = seeds, S.rng_seeds = rng_seeds;
     S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
-    S.success = succ.data(), S.ccount = cc.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
+    S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
@@ -246,7 +256,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         for(int step = 0; step < steps; step++)
         {
             // the generic kernels (BIOIK_FORCE_GENERIC=1 path of the library)
-            launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S); });
+            launch_serial(tblocks, TPB, [&]() { k_prepare(&P, S, step); });
             launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
             if(S.memetic) launch_serial(tblocks, TPB, [&]() { k_memetic(&P, S, step); });
             launch_serial(qblocks, TPB, [&]() { k_species(&P, S, step); });

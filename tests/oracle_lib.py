@@ -47,6 +47,8 @@ class Oracle:
         lib.oracle_solve_batch.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_void_p, C.c_int, dp, dp, up,
                                            C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp]
         lib.oracle_select_islands.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.c_int, C.c_int, dp, dp, dp, dp, ip, ip, C.c_int, dp, dp, ip, ip, ip]
+        lib.oracle_solve_islands.argtypes = [C.POINTER(_abi.BioikRobot), C.POINTER(_abi.BioikProblem), C.POINTER(_abi.BioikSolverCfg), C.c_void_p, C.c_int, C.c_int, dp, dp, up, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, ip, dp, dp, ip, ip]
         lib.oracle_hardware_threads.restype = C.c_int
         self._tables = {}
 
@@ -138,20 +140,21 @@ class Oracle:
         return res
 
 
-def oracle_solve_islands(o, robot, problem, cfg, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=False, wrap=True, flags=0):
-    """the oracle's statement of bioik_solve_islands: every island with Oracle.solve, then IKParallel's selection and the plugin's wrap"""
+def oracle_solve_islands(o, robot, problem, cfg, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=0, wrap=True, flags=0, nthreads=0):
+    """the oracle's statement of bioik_solve_islands (lock-step islands, IKParallel's selection, the plugin's wrap);
+    early_exit: 0 none, 1 per island, 2 per query (the reference's `finished` flag).  res["runs"] holds the per-island results."""
     seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
     Q = seeds.shape[0]
     B = Q * islands
-    gp = None if goal_params is None else np.repeat(np.ascontiguousarray(goal_params, dtype=np.float64).reshape(Q, problem.n_goals, _abi.GOAL_NPARAM), islands, axis=0)
-    sd = np.repeat(seeds, islands, axis=0)
+    gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(Q, problem.n_goals, _abi.GOAL_NPARAM)
     rs = (1 + np.arange(B)).astype(np.uint32) if rng_seeds is None else np.ascontiguousarray(rng_seeds, dtype=np.uint32).reshape(B)
-    runs = o.solve(robot, problem, cfg, gp, sd, rs, steps, early_exit=early_exit, flags=flags)
     res = dict(solutions=np.zeros((Q, robot.n_vars)), fitness=np.zeros(Q), success=np.zeros(Q, dtype=np.int32), island=np.zeros(Q, dtype=np.int32), steps=np.zeros(Q, dtype=np.int32))
+    runs = dict(solutions=np.zeros((B, robot.n_vars)), fitness=np.zeros(B), success=np.zeros(B, dtype=np.int32), steps=np.zeros(B, dtype=np.int32))
     r, p = robot.to_abi(), problem.to_abi()
-    sol, fit, succ, stp = (np.ascontiguousarray(runs[k]) for k in ("solutions", "fitness", "success", "steps"))
-    o._check(o.lib.oracle_select_islands(C.byref(r), C.byref(p), Q, islands, _abi.dptr(gp), _abi.dptr(sd), _abi.dptr(sol), _abi.dptr(fit), _abi.iptr(succ), _abi.iptr(stp), int(wrap),
-                                         _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
+    nthreads = nthreads or min(Q, os.cpu_count() or 1)
+    o._check(o.lib.oracle_solve_islands(C.byref(r), C.byref(p), C.byref(cfg), o.tables(cfg.table_seed), Q, islands, _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit), int(wrap), flags, nthreads,
+                                        _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"]),
+                                        _abi.dptr(runs["solutions"]), _abi.dptr(runs["fitness"]), _abi.iptr(runs["success"]), _abi.iptr(runs["steps"])))
     res["runs"] = runs
     return res
 

@@ -294,7 +294,7 @@ def test_mimic_joints_on_gpu(oracle):
 # ---------------------------------------------------------------------------------------------
 # islands of one query, IKParallel's selection, the plugin's angle wrap
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,Q,islands,steps,early", [("cfg2", 24, 8, 12, False), ("cfg2", 16, 5, 25, True), ("cfg4", 6, 4, 6, False), ("cfg3", 8, 3, 6, False)])
+@pytest.mark.parametrize("name,Q,islands,steps,early", [("cfg2", 24, 8, 12, 0), ("cfg2", 16, 5, 25, 1), ("cfg2", 16, 7, 25, 2), ("cfg4", 6, 4, 12, 2), ("cfg4", 6, 4, 6, 0), ("cfg3", 8, 3, 6, 0)])
 def test_solve_islands_matches_the_oracle(oracle, name, Q, islands, steps, early):
     w = workloads.make(name, ofk(oracle), batch=Q)
     solver = IKSolver(w.robot, mode="bio2_memetic", population=40, random_seed=1, device=0).initialize(w.problem)
@@ -322,8 +322,8 @@ def test_solve_islands_default_goal_parameters_and_seeds(oracle):
     rng = np.random.default_rng(2)
     seeds = workloads.sample_configurations(rm, pr.active_variables, 5, rng)
     rs = rng.integers(1, 2 ** 31 - 2, 5 * 7).astype(np.uint32)
-    got = solver.solve_islands(None, seeds, 7, 10, rng_seeds=rs)
-    ref = oracle_lib.oracle_solve_islands(oracle, rm, pr, oracle_lib.make_cfg(population=32), None, seeds, 7, 10, rng_seeds=rs)
+    got = solver.solve_islands(None, seeds, 7, 10, rng_seeds=rs, early_exit=0)
+    ref = oracle_lib.oracle_solve_islands(oracle, rm, pr, oracle_lib.make_cfg(population=32), None, seeds, 7, 10, rng_seeds=rs, early_exit=0)
     for k in ("solutions", "fitness", "success", "island", "steps"):
         assert np.array_equal(got[k], ref[k]), k
 

@@ -135,8 +135,39 @@ def test_islands_oracle_end_to_end(oracle):
     cfg = oracle_lib.make_cfg(population=18)
     res = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, 4, 8, wrap=True)
     runs = res["runs"]
+    # the lock-step island solver without early exit is just the batch solver on repeated inputs
+    plain = oracle.solve(w.robot, w.problem, cfg, np.repeat(w.goal_params, 4, 0), np.repeat(w.seeds, 4, 0), 1 + np.arange(24), 8)
+    for k in ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(plain[k], runs[k]), k
     for q in range(6):
         sl = slice(4 * q, 4 * q + 4)
         assert res["success"][q] == int(runs["success"][sl].any())
         if not runs["success"][sl].any():
             assert res["fitness"][q] == runs["fitness"][sl].min()
+
+
+def test_query_level_early_exit(oracle, sim):
+    """early_exit = 2: the reference driver's `finished` flag (src/ik_parallel.h:160-186) - once one island has passed the 4-step
+    success test, no island of that query starts another burst.  Oracle (lock-step islands) vs the simulated kernels."""
+    Q = 3
+    w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=5)
+    w.goal_params, w.seeds = w.goal_params[2:5], w.seeds[2:5]
+    cfg = oracle_lib.make_cfg(population=24)
+    islands, steps = 4, 20
+    ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=2)
+    runs = ref["runs"]
+    st = runs["steps"].reshape(Q, islands)
+    ok = runs["success"].reshape(Q, islands)
+    assert (st.max(axis=1) == st.min(axis=1)).all()           # lock step: all islands of a query stop together
+    assert (st[:, 0] < steps).any() and (st % 4 == 0).all()    # ...and before the budget is used up, at a 4-step check
+    assert (ok.sum(axis=1) > 0)[st[:, 0] < steps].all()      # a query stops early only because an island succeeded
+    gp, sd = np.repeat(w.goal_params, islands, 0), np.repeat(w.seeds, islands, 0)
+    got = sim.solve(w.robot, w.problem, cfg, gp, sd, 1 + np.arange(Q * islands), steps, early_exit=2, fast=True, islands=islands)
+    for k in ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(got[k], runs[k]), k
+    sel = sim.select_islands(w.robot, w.problem, islands, gp, sd, got, wrap=True)
+    for k in ("solutions", "fitness", "success", "island", "steps"):
+        assert np.array_equal(sel[k], ref[k]), k
+    # per-island exit lets the other islands go on: never fewer steps than with the query-level flag
+    per = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=1)
+    assert (per["runs"]["steps"] >= runs["steps"]).all()
