@@ -139,5 +139,24 @@ int main(int argc, char** argv)
         }
     std::printf("host api ok (gpu leg): %d / %d solved\n", ok, B);
     CHECK(ok > B * 8 / 10);
+    // one query at a time, 16 islands each, the reference driver's early exit and the plugin's angle wrap
+    {
+        const int Q = 8, islands = 16;
+        std::vector<double> qgp(gp.begin(), gp.begin() + Q * BIOIK_GOAL_NPARAM), qseeds(seeds.begin(), seeds.begin() + Q * n_vars);
+        std::vector<uint32_t> irs(Q * islands);
+        for(size_t i = 0; i < irs.size(); i++) irs[i] = 100 + (uint32_t)i;
+        auto ir = solver.solveIslands(qgp, qseeds, islands, irs, 25);
+        std::vector<double> at = solver.forwardKinematics(ir.solutions, 1);
+        int iok = 0;
+        for(int q = 0; q < Q; q++)
+        {
+            CHECK(ir.island[q] >= 0 && ir.island[q] < islands);
+            if(!ir.success[q]) continue;
+            iok++;
+            for(int k = 0; k < 3; k++) CHECK(std::fabs(at[q * 7 + k] - tips[q * 7 + k]) < 2e-5); // the wrapped angles are the same pose
+        }
+        std::printf("host api ok (islands): %d / %d solved\n", iok, Q);
+        CHECK(iok >= Q - 1);
+    }
     return 0;
 }
