@@ -115,6 +115,8 @@ struct DProblem
     DMimic mimics[MAX_VARS];
     int32_t dep_slot[MAX_SLOTS + MAX_GENES];
     double dep_scale[MAX_SLOTS + MAX_GENES];
+    int32_t tip_gene_start[MAX_TIPS + 1]; // genes that can move tip t (DGene::tipmask), ascending: tip_gene[tip_gene_start[t] .. tip_gene_start[t + 1])
+    int16_t tip_gene[MAX_TIPS * MAX_GENES];
     int32_t wrap_gene[MAX_GENES]; // 1: the plugin's angle wrap applies (revolute variable, robot without mimic joints; kinematics_plugin.cpp:583-584)
 };
 

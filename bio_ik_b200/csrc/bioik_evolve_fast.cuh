@@ -79,7 +79,8 @@ struct FastSmem
     __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
     __host__ __device__ int off_fit() const { return off_jq() + (nj ? 4 * FAST_MAX_JOINT_GOALS * n : 0); } // [256] primary fitness per child slot
     __host__ __device__ int off_sf() const { return off_fit() + 256; }                // [256] secondary fitness per child slot
-    __host__ __device__ int total() const { return ((off_sf() + 256) + 1) & ~1; }
+    __host__ __device__ int off_gv() const { return off_sf() + 256; }                 // [G][4 children][32 lanes] link-goal values of the tip-major form (T > 1)
+    __host__ __device__ int total() const { return ((off_gv() + (T > 1 ? G * 128 : 0)) + 1) & ~1; }
 };
 
 template <int T> BIOIK_HD void select_frame(const double (&F)[T][7], int tip, double* f)
@@ -274,11 +275,62 @@ __device__ __forceinline__ double fast_eval_one(const DProblem& P, int n, const 
     return prim;
 }
 
+// the same for any number of tips, tip by tip (only one tip's frame is live at a time); used by the tip-major kernel form
+template <bool JOINT> __device__ __forceinline__ double fast_eval_one_tips(const DProblem& P, int n, const double* x, const double* s_rec, const double* s_delta, const double* s_tip0, const double* s_gp, const double* s_jrec,
+                                                                           const double* seed)
+{
+    double gval[MAX_GOALS];
+    for(int t = 0; t < P.T; t++)
+    {
+        double F[7];
+#pragma unroll
+        for(int j = 0; j < 7; j++) F[j] = s_tip0[8 * t + j];
+        for(int idx = P.tip_gene_start[t]; idx < P.tip_gene_start[t + 1]; idx++)
+        {
+            const int i = P.tip_gene[idx];
+            const double d = x[i] - s_rec[4 * i + 1];
+            const double* D = s_delta + ((size_t)t * n + i) * 8;
+#pragma unroll
+            for(int j = 0; j < 7; j++) F[j] = BIOIK_FMA(d, D[j], F[j]);
+        }
+        for(int g = 0; g < P.G; g++)
+        {
+            const DGoal& gl = P.goals[g];
+            if(gl.secondary || gl.tip != t || (JOINT && is_joint_goal(gl.type))) continue;
+            gval[g] = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F);
+        }
+    }
+    double prim = 0.0;
+    for(int g = 0; g < P.G; g++)
+    {
+        const DGoal& gl = P.goals[g];
+        if(gl.secondary) continue;
+        double v;
+        if(JOINT && is_joint_goal(gl.type))
+        {
+            v = 0.0;
+            if(gl.type == G_JOINT_VARIABLE && gl.var_index < 0)
+            {
+                double dd = s_gp[g * GOAL_NPARAM] - seed[-1 - gl.var_index];
+                v = dd * dd;
+            }
+            else
+                for(int i = 0; i < n; i++)
+                    joint_goal_accumulate(gl.type, gl.var_index, i, x[i], s_rec[4 * i + 3], s_jrec[4 * i + 0], s_jrec[4 * i + 1], s_jrec[4 * i + 2], s_jrec[4 * i + 3], s_gp[g * GOAL_NPARAM], v);
+        }
+        else
+            v = gval[g];
+        prim += v * gl.weight_sq;
+    }
+    return prim;
+}
+
 // T = tips, CH = children evaluated together per lane (register block),
 // GSPEC = 1: the problem is exactly one primary PoseGoal (the plugin's default goal for a one-tip group);
 // JOINT: joint-space goals present (accumulated in the gene loop)
 // NG: gene count as a compile-time constant (0 = P.n at run time): the gene loop unrolls, its pointer bumps fold into immediates
-template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// TM (tip-major form, T must be 1): any number of tips P.T, one tip's frame accumulators at a time over that tip's gene list
+template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;
@@ -307,19 +359,20 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
                 nj++;
             }
 
-    FastSmem L{n, T, G, JOINT ? 1 : 0};
+    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0};
+    const int TT = TM ? P.T : T; // tips of the problem
     double* W = smem + (size_t)warp_in_block * L.total();
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
-    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
+    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf(), *s_gv = W + L.off_gv();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
 
     // ---- stage the task -------------------------------------------------------------------
-    for(int k = lane; k < T * n * 7; k += 32)
+    for(int k = lane; k < TT * n * 7; k += 32)
     {
         int ti = k / 7, c7 = k - ti * 7;
-        s_delta[ti * 8 + c7] = S.delta[(size_t)task * T * n * 7 + k];
+        s_delta[ti * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + k];
     }
-    for(int k = lane; k < T * 7; k += 32) s_tip0[(k / 7) * 8 + (k % 7)] = S.tip0[(size_t)task * T * 7 + k];
+    for(int k = lane; k < TT * 7; k += 32) s_tip0[(k / 7) * 8 + (k % 7)] = S.tip0[(size_t)task * TT * 7 + k];
     for(int i = lane; i < n; i += 32)
     {
         const DGene& Gn = P.genes[i];
@@ -375,7 +428,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
     // g+1 are the winners of generation g, whose fitness (same genes, same operations) is already known,
     // so children[0..1] (:381-388,:401-407) are evaluated once here and carried in registers afterwards.
     double pf = 0.0;
-    if(lane < 2) pf = fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
+    if(lane < 2) pf = TM ? fast_eval_one_tips<JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed) : fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
     double f_par0 = __shfl_sync(0xffffffffu, pf, 0), f_par1 = __shfl_sync(0xffffffffu, pf, 1);
 
     int cur = 0;                 // parent buffer in use
@@ -428,99 +481,171 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
 #pragma unroll
                     for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++) acc[k][j] = 0.0;
             }
-            const double* mp = mt + jbase;
-            const double* rp = s_rec;
-            const double* dp = s_delta;
-
-            // mutation terms are fetched one gene ahead of their use (L1/L2 latency off the dependent chain)
-            // (two register buffers used alternately: no register rotation in the loop)
-            double mA[CH], mB[CH];
+            if(TM)
+            {
+                // ---- tip-major form: for every tip, the FMA chain over the genes that can move it (ascending = the order of the
+                // gene-major chain restricted to that tip; the skipped genes have an all-zero delta frame, fma(d, 0, F) == F), then
+                // the link goals of that tip.  Only 7 accumulators per child are live, whatever the number of tips.
+                auto gene_value = [&](int i, int k) { // :293-297 for child k of this lane
+                    double gene = s_rec[4 * i + 0];
+                    gene += BIOIK_LDG(mt + (size_t)i * R + jbase + 32 * k); // gene += r * f
+                    gene += tp[k][6 * i];                                   // gene += gradient
+                    return clampd(gene, s_rec[4 * i + 2], s_rec[4 * i + 3]);
+                };
+                if(JOINT)
+                    for(int i = 0; i < n; i++)
+                    {
+                        double x[CH];
 #pragma unroll
-            for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + 32 * k);
-
-            // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
-            auto gene_step = [&](auto first_tag, int i, const double (&m)[CH], double (&mnext)[CH]) {
-                constexpr bool FIRST = decltype(first_tag)::value;
-                const double g0 = rp[0], base = rp[1], lo = rp[2], hi = rp[3];
-                double d[CH], x[CH];
-                mp += R;
-                if(i + 1 < n)
+                        for(int k = 0; k < CH; k++) x[k] = gene_value(i, k);
+#pragma unroll
+                        for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
+                            if(j < nj)
+                            {
+                                const double* r = s_jq + ((size_t)j * n + i) * 4;
+                                if(r[3] != 0.0)
+                                {
+                                    const double c = r[0], hs = r[1], w = r[2];
+#pragma unroll
+                                    for(int k = 0; k < CH; k++)
+                                    {
+                                        double dd = x[k] - c;
+                                        if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
+                                        dd *= w;
+                                        acc[k][j] += dd * dd;
+                                    }
+                                }
+                            }
+                    }
+                for(int t = 0; t < TT; t++)
                 {
-#pragma unroll
-                    for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
-                }
-#pragma unroll
-                for(int k = 0; k < CH; k++)
-                {
-                    double gene = g0;
-                    gene += m[k];                // gene += r * f      (:293)
-                    gene += tp[k][0];            // gene += gradient   (:296)
-                    gene = clampd(gene, lo, hi); // :297
-                    x[k] = gene;
-                    d[k] = gene - base; // :1086
-                    tp[k] += 6;
-                }
-                rp += 4;
-                const int tmask = (T == 1) ? 1 : P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
-#pragma unroll
-                for(int t = 0; t < T; t++)
-                {
-                    const bool on = (tmask >> t) & 1;
-                    if(!on && !FIRST) continue; // fma(d, 0, F) == F
-                    const double* D = dp + (size_t)t * n * 8;
-                    double Dv[7];
-#pragma unroll
-                    for(int j = 0; j < 7; j++) Dv[j] = on ? D[j] : 0.0;
 #pragma unroll
                     for(int k = 0; k < CH; k++)
 #pragma unroll
-                        for(int j = 0; j < 7; j++) F[k][t][j] = BIOIK_FMA(d[k], Dv[j], FIRST ? s_tip0[8 * t + j] : F[k][t][j]);
-                }
-                dp += 8;
-                if(JOINT)
-                {
+                        for(int j = 0; j < 7; j++) F[k][0][j] = s_tip0[8 * t + j];
+                    const int i1 = P.tip_gene_start[t + 1];
+                    for(int idx = P.tip_gene_start[t]; idx < i1; idx++)
+                    {
+                        const int i = P.tip_gene[idx];
+                        const double base = s_rec[4 * i + 1];
+                        const double* D = s_delta + ((size_t)t * n + i) * 8;
+                        double Dv[7];
 #pragma unroll
-                    for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
-                        if(j < nj)
+                        for(int j = 0; j < 7; j++) Dv[j] = D[j];
+#pragma unroll
+                        for(int k = 0; k < CH; k++)
                         {
-                            const double* r = s_jq + ((size_t)j * n + i) * 4;
-                            if(r[3] != 0.0) // warp-uniform: the goal applies to this gene
-                            {
-                                const double c = r[0], hs = r[1], w = r[2];
+                            const double d = gene_value(i, k) - base; // :1086
 #pragma unroll
-                                for(int k = 0; k < CH; k++)
-                                {
-                                    double dd = x[k] - c;
-                                    if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
-                                    dd *= w;
-                                    acc[k][j] += dd * dd;
-                                }
-                            }
+                            for(int j = 0; j < 7; j++) F[k][0][j] = BIOIK_FMA(d, Dv[j], F[k][0][j]);
                         }
-                }
-            };
-            gene_step(std::true_type{}, 0, mA, mB);
-            if(NG)
-            {
+                    }
+                    for(int g = 0; g < G; g++)
+                    {
+                        const DGoal& gl = P.goals[g];
+                        if(gl.secondary || gl.tip != t || is_joint_goal(gl.type)) continue;
 #pragma unroll
-                for(int i = 1; i < NG; i++)
-                {
-                    if(i & 1)
-                        gene_step(std::false_type{}, i, mB, mA);
-                    else
-                        gene_step(std::false_type{}, i, mA, mB);
+                        for(int k = 0; k < CH; k++) s_gv[((size_t)g * 4 + k) * 32 + lane] = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F[k][0]);
+                    }
                 }
             }
             else
             {
-                int i = 1;
-#pragma unroll 1
-                for(; i + 1 < n; i += 2)
+                const double* mp = mt + jbase;
+                const double* rp = s_rec;
+                const double* dp = s_delta;
+
+                // mutation terms are fetched one gene ahead of their use (L1/L2 latency off the dependent chain)
+                // (two register buffers used alternately: no register rotation in the loop)
+                double mA[CH], mB[CH];
+    #pragma unroll
+                for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + 32 * k);
+
+                // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
+                auto gene_step = [&](auto first_tag, int i, const double (&m)[CH], double (&mnext)[CH]) {
+                    constexpr bool FIRST = decltype(first_tag)::value;
+                    const double g0 = rp[0], base = rp[1], lo = rp[2], hi = rp[3];
+                    double d[CH], x[CH];
+                    mp += R;
+                    if(i + 1 < n)
+                    {
+    #pragma unroll
+                        for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
+                    }
+    #pragma unroll
+                    for(int k = 0; k < CH; k++)
+                    {
+                        double gene = g0;
+                        gene += m[k];                // gene += r * f      (:293)
+                        gene += tp[k][0];            // gene += gradient   (:296)
+                        gene = clampd(gene, lo, hi); // :297
+                        x[k] = gene;
+                        d[k] = gene - base; // :1086
+                        tp[k] += 6;
+                    }
+                    rp += 4;
+                    const int tmask = (T == 1) ? 1 : P.genes[i].tipmask; // tips this gene can move (structural); others have an all-zero delta frame
+    #pragma unroll
+                    for(int t = 0; t < T; t++)
+                    {
+                        const bool on = (tmask >> t) & 1;
+                        if(!on && !FIRST) continue; // fma(d, 0, F) == F
+                        const double* D = dp + (size_t)t * n * 8;
+                        double Dv[7];
+    #pragma unroll
+                        for(int j = 0; j < 7; j++) Dv[j] = on ? D[j] : 0.0;
+    #pragma unroll
+                        for(int k = 0; k < CH; k++)
+    #pragma unroll
+                            for(int j = 0; j < 7; j++) F[k][t][j] = BIOIK_FMA(d[k], Dv[j], FIRST ? s_tip0[8 * t + j] : F[k][t][j]);
+                    }
+                    dp += 8;
+                    if(JOINT)
+                    {
+    #pragma unroll
+                        for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
+                            if(j < nj)
+                            {
+                                const double* r = s_jq + ((size_t)j * n + i) * 4;
+                                if(r[3] != 0.0) // warp-uniform: the goal applies to this gene
+                                {
+                                    const double c = r[0], hs = r[1], w = r[2];
+    #pragma unroll
+                                    for(int k = 0; k < CH; k++)
+                                    {
+                                        double dd = x[k] - c;
+                                        if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
+                                        dd *= w;
+                                        acc[k][j] += dd * dd;
+                                    }
+                                }
+                            }
+                    }
+                };
+                gene_step(std::true_type{}, 0, mA, mB);
+                if(NG)
                 {
-                    gene_step(std::false_type{}, i, mB, mA);
-                    gene_step(std::false_type{}, i + 1, mA, mB);
+    #pragma unroll
+                    for(int i = 1; i < NG; i++)
+                    {
+                        if(i & 1)
+                            gene_step(std::false_type{}, i, mB, mA);
+                        else
+                            gene_step(std::false_type{}, i, mA, mB);
+                    }
                 }
-                if(i < n) gene_step(std::false_type{}, i, mB, mA);
+                else
+                {
+                    int i = 1;
+    #pragma unroll 1
+                    for(; i + 1 < n; i += 2)
+                    {
+                        gene_step(std::false_type{}, i, mB, mA);
+                        gene_step(std::false_type{}, i + 1, mA, mB);
+                    }
+                    if(i < n) gene_step(std::false_type{}, i, mB, mA);
+                }
+
             }
 
             // fitness: weighted sum in goal order (src/problem.cpp:251-257)
@@ -553,15 +678,20 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0> __global__ void __la
                         }
                         else
                         {
-                            double f[7];
-                            select_frame<T>(F[k], gl.secondary ? 0 : gl.tip, f);
-                            if(gl.secondary)
+                            if(TM && !gl.secondary)
+                                v = s_gv[((size_t)g * 4 + k) * 32 + lane]; // evaluated when the tip's frame was complete
+                            else
                             {
-                                // secondary goals see null_tip_frames (identity), src/ik_base.h:163
-                                f[0] = f[1] = f[2] = f[3] = f[4] = f[5] = 0.0;
-                                f[6] = 1.0;
+                                double f[7];
+                                select_frame<T>(F[k], gl.secondary ? 0 : gl.tip, f);
+                                if(gl.secondary)
+                                {
+                                    // secondary goals see null_tip_frames (identity), src/ik_base.h:163
+                                    f[0] = f[1] = f[2] = f[3] = f[4] = f[5] = 0.0;
+                                    f[6] = 1.0;
+                                }
+                                v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
                             }
-                            v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
                         }
                         if(gl.secondary)
                             sec += v * gl.weight_sq;
@@ -747,17 +877,12 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     if(single_pose && cpl >= 3 && P.n == 7 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>;
     if(single_pose && cpl >= 3 && P.n == 6 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>;
     if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
-    switch(T)
-    {
-    case 1: return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));
-    case 2: return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1);
-    case 3: return cpl >= 2 ? BIOIK_PICK(3, 2) : BIOIK_PICK(3, 1);
-    case 4: return BIOIK_PICK(4, 1);
-    case 5: return BIOIK_PICK(5, 1);
-    case 6: return BIOIK_PICK(6, 1);
-    case 7: return BIOIK_PICK(7, 1);
-    default: return BIOIK_PICK(8, 1);
-    }
+    if(T == 1) return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));
+    if(T == 2) return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1); // two tips still fit the gene-major register block (cfg3: 9.9 vs 10.1 ms per pass)
+    // three or more tips: the tip-major form (one tip's accumulators at a time, so the register block does not depend on T; cfg5: 54.7 vs 57.6 ms)
+#define BIOIK_PICK_TM(CC) (J ? (EvolveFastKernel)k_evolve_fast<1, CC, 0, true, 0, true> : (EvolveFastKernel)k_evolve_fast<1, CC, 0, false, 0, true>)
+    return cpl >= 3 ? BIOIK_PICK_TM(4) : (cpl == 2 ? BIOIK_PICK_TM(2) : BIOIK_PICK_TM(1));
+#undef BIOIK_PICK_TM
 #undef BIOIK_PICK
 }
 

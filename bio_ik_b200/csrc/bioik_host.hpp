@@ -240,6 +240,17 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
             }
     }
     {
+        // per-tip gene lists of the tip-major generation kernel
+        int k = 0;
+        for(int t = 0; t < P.T; t++)
+        {
+            P.tip_gene_start[t] = k;
+            for(int i = 0; i < p->n_active; i++)
+                if((P.genes[i].tipmask >> t) & 1) P.tip_gene[k++] = (int16_t)i;
+        }
+        for(int t = P.T; t <= MAX_TIPS; t++) P.tip_gene_start[t] = k;
+    }
+    {
         // kinematics_plugin.cpp:583-584: the angle wrap applies to revolute variables of robots without mimic joints
         bool any_mimic = false;
         for(int l = 0; l < R.n_links; l++) any_mimic = any_mimic || R.mimic[l] >= 0;
