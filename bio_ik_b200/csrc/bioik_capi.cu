@@ -39,6 +39,7 @@ struct bioik_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t stream_evolve = nullptr, stream_serial = nullptr; // internal streams of the two-half pipeline
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_evolve[2] = {nullptr, nullptr}, ev_serial[2] = {nullptr, nullptr};
+    int lpt_want = 16; // BIOIK_EVOLVE_LPT: lanes per task of the single-pose generation kernel (8, 16 or 32; measured 7.15 / 6.98 / 7.22 ms per cfg2 pass)
     int ch_cap = 8; // BIOIK_EVOLVE_CH: cap of the register block of k_evolve_fast (experiments)
     bool pipeline = false; // BIOIK_PIPELINE=1 enables the two-half overlap (experimental)
     std::string error;
@@ -347,13 +348,15 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
 
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    const int warps_per_block = 4;
-    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap);
+    const int warps_per_block = BIOIK_EVOLVE_WPB;
+    int evolve_lpt = 32; // lanes per task of the generation kernel
+    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &evolve_lpt, ctx->lpt_want);
+    const int evolve_tpw = 32 / evolve_lpt; // tasks per warp
     size_t smem;
     if(fast)
     {
-        FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0};
-        smem = (size_t)warps_per_block * L.total() * sizeof(double);
+        FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1};
+        smem = (size_t)warps_per_block * evolve_tpw * L.total() * sizeof(double);
         if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     else
@@ -430,7 +433,8 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
             return r;
         };
         auto launch_evolve = [&](int h, int step) -> int {
-            const int eb = (2 * Sh[h].B + warps_per_block - 1) / warps_per_block;
+            const int tasks_per_block = warps_per_block * (fast ? evolve_tpw : 1);
+            const int eb = (2 * Sh[h].B + tasks_per_block - 1) / tasks_per_block;
             if(H == 2) cudaStreamWaitEvent(se, ctx->ev_serial[h], 0);
             Timed tm(ctx, se, 0);
             if(fast)
@@ -582,6 +586,8 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         ctx->force_generic = fg && fg[0] == '1';
         const char* ng = getenv("BIOIK_NO_GRAPH");
         ctx->use_graphs = !(ng && ng[0] == '1');
+        const char* lp = getenv("BIOIK_EVOLVE_LPT");
+        if(lp && atoi(lp) > 0) ctx->lpt_want = atoi(lp);
         const char* ch = getenv("BIOIK_EVOLVE_CH");
         if(ch && atoi(ch) > 0) ctx->ch_cap = atoi(ch);
         const char* mg = getenv("BIOIK_MEMETIC_GROUP");

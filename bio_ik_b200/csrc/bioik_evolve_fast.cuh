@@ -68,6 +68,7 @@ __global__ void k_mutation_table(const DProblem* __restrict__ Pp, int calls, int
 struct FastSmem
 {
     int n, T, G, nj;
+    int lean = 0; // 1: no per-child fitness arrays (only the pre-selection of problems with secondary goals reads them)
     __host__ __device__ int off_rec() const { return 0; }                        // [n][4]  g0, base, clip_min, clip_max
     __host__ __device__ int off_term() const { return off_rec() + 4 * n; }       // [n][6]  pg[parity] * gradient_factor
     __host__ __device__ int off_delta() const { return off_term() + 6 * n; }     // [T][n][8]
@@ -78,8 +79,8 @@ struct FastSmem
     __host__ __device__ int off_jrec() const { return off_gp() + 12 * G; }       // [n][4]  mid, halfspan, vel_weight, seed  (nj > 0)
     __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
     __host__ __device__ int off_fit() const { return off_jq() + (nj ? 4 * FAST_MAX_JOINT_GOALS * n : 0); } // [256] primary fitness per child slot
-    __host__ __device__ int off_sf() const { return off_fit() + 256; }                // [256] secondary fitness per child slot
-    __host__ __device__ int off_gv() const { return off_sf() + 256; }                 // [G][4 children][32 lanes] link-goal values of the tip-major form (T > 1)
+    __host__ __device__ int off_sf() const { return off_fit() + (lean ? 0 : 256); }   // [256] secondary fitness per child slot
+    __host__ __device__ int off_gv() const { return off_sf() + (lean ? 0 : 256); }                 // [G][4 children][32 lanes] link-goal values of the tip-major form (T > 1)
     __host__ __device__ int total() const { return ((off_gv() + (T > 1 ? G * 128 : 0)) + 1) & ~1; }
 };
 
@@ -207,19 +208,23 @@ BIOIK_HD void joint_goal_accumulate(int type, int var_index, int i, double x, do
 }
 
 // warp argmin of (fitness key, packed position/child) with three REDUX.MIN: ties -> lowest position (:419-423)
-__device__ __forceinline__ uint32_t fast_warp_argmin(uint64_t key, uint32_t packed)
+// (over the lanes of `mask`: the whole warp, or the aligned lane group of one task)
+__device__ __forceinline__ uint32_t fast_warp_argmin(uint64_t key, uint32_t packed, unsigned mask = 0xffffffffu)
 {
     uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-    uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+    uint32_t mh = __reduce_min_sync(mask, hi);
     uint32_t l2 = (hi == mh) ? lo : 0xFFFFFFFFu;
-    uint32_t ml = __reduce_min_sync(0xffffffffu, l2);
+    uint32_t ml = __reduce_min_sync(mask, l2);
     uint32_t p2 = (hi == mh && lo == ml) ? packed : 0xFFFFFFFFu;
-    return __reduce_min_sync(0xffffffffu, p2);
+    return __reduce_min_sync(mask, p2);
 }
 __device__ __forceinline__ uint64_t fast_fitness_key(double f) { return (f != f) ? 0xFFFFFFFFFFFFFFFEull : (uint64_t)__double_as_longlong(f); }
 constexpr uint64_t FAST_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
 __device__ __forceinline__ bool key_less(uint64_t ka, uint32_t pa, uint64_t kb, uint32_t pb) { return ka < kb || (ka == kb && pa < pb); }
 
+#ifndef BIOIK_EVOLVE_WPB
+#define BIOIK_EVOLVE_WPB 4 // warps per block of the generation kernels
+#endif
 #ifndef BIOIK_EVOLVE_MINBLOCKS
 #define BIOIK_EVOLVE_MINBLOCKS 4
 #endif
@@ -330,19 +335,27 @@ template <bool JOINT> __device__ __forceinline__ double fast_eval_one_tips(const
 // JOINT: joint-space goals present (accumulated in the gene loop)
 // NG: gene count as a compile-time constant (0 = P.n at run time): the gene loop unrolls, its pointer bumps fold into immediates
 // TM (tip-major form, T must be 1): any number of tips P.T, one tip's frame accumulators at a time over that tip's gene list
-template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __global__ void __launch_bounds__(128, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// LPT (lanes per task): 32 = one warp per task; 16 / 8 = two / four tasks per warp, each lane then owns 8 / 16 children.  The
+// per-child work is lane-efficient either way, but the per-generation overhead (tables, the two argmin reductions, winner
+// re-derivation: ~37 % of the instructions at LPT 32) is issued once per WARP, i.e. shared by the tasks of the warp.
+template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int LPT = 32> __global__ void __launch_bounds__(32 * BIOIK_EVOLVE_WPB, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;
-    const int lane = threadIdx.x & 31;
+    static_assert(LPT == 32 || (LPT == 16 || LPT == 8) && !TM && GSPEC == 1 && !JOINT, "lane groups are instantiated for the single-pose problem only");
+    constexpr int TPW = 32 / LPT;            // tasks per warp
+    const int lane = (threadIdx.x & 31) % LPT; // lane within the task's group
+    const int grp = (threadIdx.x & 31) / LPT;
+    const int lane0 = grp * LPT;             // first warp lane of the group
+    const unsigned gmask = LPT == 32 ? 0xffffffffu : (((1u << LPT) - 1u) << lane0); // the group's lanes: every warp-level primitive below is group-wide
     const int warp_in_block = threadIdx.x >> 5;
-    const int task = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    const int task = (blockIdx.x * (blockDim.x >> 5) + warp_in_block) * TPW + grp;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
     if(run_done(S, q, step)) return;
     const int n = NG ? NG : P.n, C = S.C, G = P.G;
     const int R = mtab_row(C);
-    const int nchunks = R / (32 * CH); // R is a power of two >= 32 * CH (select_evolve_fast)
+    const int nchunks = R / (LPT * CH); // R is a power of two >= LPT * CH (select_evolve_fast)
 
     // joint-space goals in goal order: slot j of the accumulators = the j-th of them; avoid_j = AvoidJointLimitsGoal
     int nj = 0;
@@ -359,21 +372,21 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
                 nj++;
             }
 
-    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0};
+    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1};
     const int TT = TM ? P.T : T; // tips of the problem
-    double* W = smem + (size_t)warp_in_block * L.total();
+    double* W = smem + (size_t)(warp_in_block * TPW + grp) * L.total();
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
     double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf(), *s_gv = W + L.off_gv();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
 
     // ---- stage the task -------------------------------------------------------------------
-    for(int k = lane; k < TT * n * 7; k += 32)
+    for(int k = lane; k < TT * n * 7; k += LPT)
     {
         int ti = k / 7, c7 = k - ti * 7;
         s_delta[ti * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + k];
     }
-    for(int k = lane; k < TT * 7; k += 32) s_tip0[(k / 7) * 8 + (k % 7)] = S.tip0[(size_t)task * TT * 7 + k];
-    for(int i = lane; i < n; i += 32)
+    for(int k = lane; k < TT * 7; k += LPT) s_tip0[(k / 7) * 8 + (k % 7)] = S.tip0[(size_t)task * TT * 7 + k];
+    for(int i = lane; i < n; i += LPT)
     {
         const DGene& Gn = P.genes[i];
         s_rec[4 * i + 1] = S.base[(size_t)task * n + i];
@@ -391,8 +404,8 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             s_jrec[4 * i + 3] = seed[Gn.var];
         }
     }
-    for(int k = lane; k < G * GOAL_NPARAM; k += 32) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
-    __syncwarp();
+    for(int k = lane; k < G * GOAL_NPARAM; k += LPT) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
+    __syncwarp(gmask);
     if(JOINT)
     {
         // One record per (joint-space goal, gene): every such goal adds ((x - centre) [-> max(0, |.| * 2 - half span)]) * weight,
@@ -403,7 +416,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
         {
             const DGoal& gl = P.goals[g];
             if(!is_joint_goal(gl.type) || j >= FAST_MAX_JOINT_GOALS) continue;
-            for(int i = lane; i < n; i += 32)
+            for(int i = lane; i < n; i += LPT)
             {
                 const DGene& Gn = P.genes[i];
                 double c = 0.0, w = 1.0, on = 1.0;
@@ -421,7 +434,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             }
             j++;
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
 
     // Fitness of the two parents under this step's approximator.  Within a step the parents of generation
@@ -429,7 +442,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
     // so children[0..1] (:381-388,:401-407) are evaluated once here and carried in registers afterwards.
     double pf = 0.0;
     if(lane < 2) pf = TM ? fast_eval_one_tips<JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed) : fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
-    double f_par0 = __shfl_sync(0xffffffffu, pf, 0), f_par1 = __shfl_sync(0xffffffffu, pf, 1);
+    double f_par0 = __shfl_sync(gmask, pf, lane0 + 0), f_par1 = __shfl_sync(gmask, pf, lane0 + 1);
 
     int cur = 0;                 // parent buffer in use
     const int parity = lane & 1; // child slot c = j + 2 is even <=> lane is even
@@ -444,7 +457,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
         const double *p_g0 = par, *p_g1 = par + n, *p_gr0 = par + 2 * n, *p_gr1 = par + 3 * n;
 
         // per-generation warp-uniform tables: pg = mix(gr0, gr1, fmix), term = pg * gradient_factor  (:268-269,:294-295)
-        for(int i = lane; i < n; i += 32)
+        for(int i = lane; i < n; i += LPT)
         {
             double a = p_gr0[i], b = p_gr1[i];
             double pge = mix(a, b, 0.2); // child_index even: fmix = 1 * 0.2
@@ -459,7 +472,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             s_term[6 * i + 5] = pgo * 2.0;
             s_rec[4 * i + 0] = p_g0[i];
         }
-        __syncwarp();
+        __syncwarp(gmask);
 
         // this lane's two best children so far: (key, packed = position * 512 + child)
         uint64_t k1 = FAST_KEY_NONE, k2 = FAST_KEY_NONE;
@@ -468,14 +481,14 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
 
         for(int chunk = 0; chunk < nchunks; chunk++)
         {
-            const int jbase = lane + 32 * CH * chunk; // child slot c = j + 2
+            const int jbase = lane + LPT * CH * chunk; // child slot c = j + 2
             double F[CH][T][7];
             double acc[JOINT ? CH : 1][FAST_MAX_JOINT_GOALS];
             const double* tp[CH]; // term column of each child: fmix class x gradient_factor (c % 3)
 #pragma unroll
             for(int k = 0; k < CH; k++)
             {
-                int c = jbase + 32 * k + 2;
+                int c = jbase + LPT * k + 2;
                 tp[k] = s_term + (parity ? 3 : 0) + (c % 3);
                 if(JOINT)
 #pragma unroll
@@ -488,7 +501,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
                 // the link goals of that tip.  Only 7 accumulators per child are live, whatever the number of tips.
                 auto gene_value = [&](int i, int k) { // :293-297 for child k of this lane
                     double gene = s_rec[4 * i + 0];
-                    gene += BIOIK_LDG(mt + (size_t)i * R + jbase + 32 * k); // gene += r * f
+                    gene += BIOIK_LDG(mt + (size_t)i * R + jbase + LPT * k); // gene += r * f
                     gene += tp[k][6 * i];                                   // gene += gradient
                     return clampd(gene, s_rec[4 * i + 2], s_rec[4 * i + 3]);
                 };
@@ -559,7 +572,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
                 // (two register buffers used alternately: no register rotation in the loop)
                 double mA[CH], mB[CH];
     #pragma unroll
-                for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + 32 * k);
+                for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + LPT * k);
 
                 // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
                 auto gene_step = [&](auto first_tag, int i, const double (&m)[CH], double (&mnext)[CH]) {
@@ -570,7 +583,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
                     if(i + 1 < n)
                     {
     #pragma unroll
-                        for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + 32 * k);
+                        for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mp + LPT * k);
                     }
     #pragma unroll
                     for(int k = 0; k < CH; k++)
@@ -652,7 +665,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
 #pragma unroll
             for(int k = 0; k < CH; k++)
             {
-                const int c = jbase + 32 * k + 2;
+                const int c = jbase + LPT * k + 2;
                 double prim = 0.0, sec = 0.0;
                 if(GSPEC == 1)
                     prim += link_goal_value(G_POSE, s_gp, F[k][0]) * wsq0;
@@ -736,7 +749,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
         {
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
-            __syncwarp();
+            __syncwarp(gmask);
 #pragma unroll 1
             for(int k = 0; k < FAST_MAX_CPL; k++)
             {
@@ -773,7 +786,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
             if(lane == 0 && key_less(kp0, 0u, kk, pk)) { kk = kp0; pk = 0u; }
             if(lane == 1 && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
-            w1 = fast_warp_argmin(kk, pk);
+            w1 = fast_warp_argmin(kk, pk, gmask);
             if(f_par0 != f_par0) w1 = 0u; // position 0 holds a NaN: `f < fmin` never fires (:418-422)
         }
         const uint32_t w1_pos = w1 >> 9, w1_child = w1 & 511u;
@@ -786,7 +799,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
             if(lane == 0 && w1_child != 0u && key_less(kp0, w1_pos * 512u, kk, pk)) { kk = kp0; pk = w1_pos * 512u; }
             if(lane == 1 && w1_child != 1u && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
-            w2 = fast_warp_argmin(kk, pk);
+            w2 = fast_warp_argmin(kk, pk, gmask);
             // the scan starts at position 1: its occupant wins if its fitness is NaN
             uint32_t occ1 = (w1_pos == 1u) ? 0u : 1u;
             double f_occ1 = occ1 == 0u ? f_par0 : f_par1;
@@ -799,17 +812,17 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
             uint64_t kw1 = (k1 != FAST_KEY_NONE && q1 == w1) ? k1 : 0ull;
             uint64_t kw2 = (k1 != FAST_KEY_NONE && q1 == w2) ? k1 : ((k2 != FAST_KEY_NONE && q2 == w2) ? k2 : 0ull);
             // exactly one lane holds each child winner; parents keep their cached value
-            uint32_t own1 = __ballot_sync(0xffffffffu, w1_child >= 2u && q1 == w1);
-            uint32_t own2 = __ballot_sync(0xffffffffu, w2_child >= 2u && (q1 == w2 || q2 == w2));
+            uint32_t own1 = __ballot_sync(gmask, w1_child >= 2u && q1 == w1);
+            uint32_t own2 = __ballot_sync(gmask, w2_child >= 2u && (q1 == w2 || q2 == w2));
             double nf0 = w1_child == 0u ? f_par0 : f_par1, nf1 = w2_child == 0u ? f_par0 : f_par1;
             if(own1)
             {
-                uint64_t kb = __shfl_sync(0xffffffffu, kw1, __ffs(own1) - 1);
+                uint64_t kb = __shfl_sync(gmask, kw1, __ffs(own1) - 1);
                 nf0 = __longlong_as_double((long long)kb);
             }
             if(own2)
             {
-                uint64_t kb = __shfl_sync(0xffffffffu, kw2, __ffs(own2) - 1);
+                uint64_t kb = __shfl_sync(gmask, kw2, __ffs(own2) - 1);
                 nf1 = __longlong_as_double((long long)kb);
             }
             f_par0 = nf0;
@@ -820,7 +833,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
         double* nxt = s_par + (cur ^ 1) * 4 * n;
         {
             const int wc1 = (int)w1_child, wc2 = (int)w2_child;
-            for(int i = lane; i < n; i += 32)
+            for(int i = lane; i < n; i += LPT)
             {
                 const double g0 = p_g0[i], lo = s_rec[4 * i + 2], hi = s_rec[4 * i + 3];
 #pragma unroll
@@ -847,12 +860,12 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
                 }
             }
         }
-        __syncwarp();
+        __syncwarp(gmask);
         cur ^= 1;
     }
 
     double* par = s_par + cur * 4 * n;
-    for(int i = lane; i < n; i += 32)
+    for(int i = lane; i < n; i += LPT)
     {
         S.genes[((size_t)task * 2 + 0) * n + i] = par[i];
         S.genes[((size_t)task * 2 + 1) * n + i] = par[n + i];
@@ -864,9 +877,11 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false> __g
 typedef void (*EvolveFastKernel)(const DProblem*, DState, int, const double*);
 
 // picks the instantiation for (tips, population, goals); returns nullptr if the generic kernel must be used
-inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap = 8)
+// *lanes_per_task (if given) receives the lane-group width of the returned kernel: the launch has 32 / width tasks per warp
+inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap = 8, int* lanes_per_task = nullptr, int lpt_want = 16)
 {
     const int T = P.T;
+    if(lanes_per_task) *lanes_per_task = 32;
     if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
     const bool J = P.n_joint_goals > 0;
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);
@@ -874,8 +889,14 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
     if(J && cpl > 2) cpl = 2;      // joint-space accumulators on top of the frame accumulators: blocks of 4 spill (cfg4: 29.5 vs 21.8 ms per pass)
 #define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
-    if(single_pose && cpl >= 3 && P.n == 7 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>;
-    if(single_pose && cpl >= 3 && P.n == 6 && ch_cap >= 8) return (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>;
+    if(single_pose && cpl >= 3 && (P.n == 7 || P.n == 6) && ch_cap >= 8)
+    {
+        // lane groups: R / (LPT * 4) chunks of 4 children per lane; R >= 128 here
+        const int lpt = lanes_per_task ? (lpt_want <= 8 ? 8 : (lpt_want <= 16 ? 16 : 32)) : 32;
+        if(lanes_per_task) *lanes_per_task = lpt;
+        if(P.n == 7) return lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>);
+        return lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>);
+    }
     if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
     if(T == 1) return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));
     if(T == 2) return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1); // two tips still fit the gene-major register block (cfg3: 9.9 vs 10.1 ms per pass)

@@ -33,38 +33,45 @@ static sim_uint3 blockDim, gridDim;
 namespace bioik { double smem[1 << 18]; } // the `extern __shared__ double smem[]` of k_evolve
 
 static std::barrier<>* g_warp_barrier = nullptr;
+// barriers of the aligned lane groups (16- and 8-lane masks): kernels that put several tasks in a warp synchronise per group
+static std::barrier<>* g_group_barrier[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
 static uint64_t g_shfl_slots[32];
-static inline void __syncwarp() { g_warp_barrier->arrive_and_wait(); }
-template <class T> static inline T sim_shfl(T v, int src)
+static inline std::barrier<>& sim_barrier(unsigned mask)
+{
+    if(mask == 0xffffffffu) return *g_warp_barrier;
+    const int width = __builtin_popcount(mask), first = __builtin_ctz(mask);
+    return *g_group_barrier[width == 16 ? 0 : 1][first / width];
+}
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { sim_barrier(mask).arrive_and_wait(); }
+template <class T> static inline T sim_shfl(T v, int src, unsigned mask = 0xffffffffu)
 {
     static_assert(sizeof(T) <= 8, "");
     uint64_t raw = 0;
     memcpy(&raw, &v, sizeof(T));
     g_shfl_slots[threadIdx.x & 31] = raw;
-    g_warp_barrier->arrive_and_wait();
+    sim_barrier(mask).arrive_and_wait();
     uint64_t got = g_shfl_slots[src & 31];
-    g_warp_barrier->arrive_and_wait();
+    sim_barrier(mask).arrive_and_wait();
     T r;
     memcpy(&r, &got, sizeof(T));
     return r;
 }
-template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return sim_shfl(v, (int)(threadIdx.x & 31) ^ o); }
-template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return sim_shfl(v, src); }
-static inline unsigned sim_reduce_min(unsigned v)
+template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int o) { return sim_shfl(v, (int)(threadIdx.x & 31) ^ o, m); }
+template <class T> static inline T __shfl_sync(unsigned m, T v, int src) { return sim_shfl(v, src, m); }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
 {
     unsigned m = v;
-    for(int o = 16; o > 0; o >>= 1)
+    for(int o = __builtin_popcount(mask) / 2; o > 0; o >>= 1) // butterfly inside the aligned group
     {
-        unsigned other = sim_shfl(m, (int)(threadIdx.x & 31) ^ o);
+        unsigned other = sim_shfl(m, (int)(threadIdx.x & 31) ^ o, mask);
         m = other < m ? other : m;
     }
     return m;
 }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return sim_reduce_min(v); }
-static inline unsigned __ballot_sync(unsigned, bool pred)
+static inline unsigned __ballot_sync(unsigned mask, bool pred)
 {
     unsigned bit = pred ? (1u << (threadIdx.x & 31)) : 0u, acc = bit;
-    for(int o = 16; o > 0; o >>= 1) acc |= sim_shfl(acc, (int)(threadIdx.x & 31) ^ o);
+    for(int o = __builtin_popcount(mask) / 2; o > 0; o >>= 1) acc |= sim_shfl(acc, (int)(threadIdx.x & 31) ^ o, mask);
     return acc;
 }
 static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
@@ -114,6 +121,10 @@ template <class F> void launch_warp(int blocks, F f)
     gridDim.x = blocks;
     std::barrier<> bar(32);
     g_warp_barrier = &bar;
+    std::barrier<> b16[2] = {std::barrier<>(16), std::barrier<>(16)};
+    std::barrier<> b8[4] = {std::barrier<>(8), std::barrier<>(8), std::barrier<>(8), std::barrier<>(8)};
+    for(int i = 0; i < 2; i++) g_group_barrier[0][i] = &b16[i];
+    for(int i = 0; i < 4; i++) g_group_barrier[1][i] = &b8[i];
     std::vector<std::thread> lanes;
     for(int l = 0; l < 32; l++)
         lanes.emplace_back([&, l]() {
@@ -169,6 +180,10 @@ void hostsim_sincos(int n, const double* x, double* s, double* c)
     for(int i = 0; i < n; i++) d_sincos(x[i], s[i], c[i]);
 }
 
+// lanes per task wanted for the single-pose generation kernel (8, 16, 32)
+static int g_lpt_want = 16;
+void hostsim_set_evolve_lanes(int lpt) { g_lpt_want = lpt; }
+
 // islands per query of the next hostsim_solve calls (0: plain batch), for early_exit == 2
 static int g_islands = 0;
 void hostsim_set_islands(int islands) { g_islands = islands; }
@@ -208,7 +223,8 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    EvolveFastKernel fast = use_fast ? select_evolve_fast(P, S.C) : nullptr;
+    int evolve_lpt = 32;
+    EvolveFastKernel fast = use_fast ? select_evolve_fast(P, S.C, 8, &evolve_lpt, g_lpt_want) : nullptr;
     if(use_fast && !fast)
     {
         g_err = "no fast kernel instantiation for this problem";
@@ -240,7 +256,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         if(steps > 0) launch_warp(sgrid, [&]() { ks(P, S, 0, PH_PREPARE); });
         for(int step = 0; step < steps; step++)
         {
-            launch_warp(2 * B, [&]() { fast(&P, S, step, mtab.data()); });
+            launch_warp((2 * B + 32 / evolve_lpt - 1) / (32 / evolve_lpt), [&]() { fast(&P, S, step, mtab.data()); });
             int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
             if(group_memetic && S.memetic)
             {

@@ -63,6 +63,19 @@ def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B,
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_generation_kernel_lane_groups(sim, oracle, lanes):
+    """k_evolve_fast with 8 / 16 / 32 lanes per task (4 / 2 / 1 tasks per warp) on the single-pose problem: an odd task count
+    leaves lane groups of the last warp without work, early exit retires groups of a warp at different steps."""
+    w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=5)
+    for pop, steps, early in ((128, 3, False), (200, 2, False), (128, 12, True)):
+        cfg = oracle_lib.make_cfg(population=pop)
+        a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, early_exit=early)
+        b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, early_exit=early, fast=True, evolve_lanes=lanes)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps") if not early else ("solutions", "fitness", "success", "steps"):
+            assert np.array_equal(a[k], b[k]), (k, pop)
+
+
 @pytest.mark.parametrize("name,B,pop,mode,steps,variant", [("cfg2", 5, 18, "q", 6, 6), ("cfg2", 3, 40, "l", 4, 6), ("cfg2", 3, 18, "q", 3, 9), ("cfg3", 3, 40, "q", 3, 6), ("cfg3", 1, 20, "q", 2, 7),
                                                             ("cfg4", 2, 40, "q", 2, 6), ("cfg4", 1, 20, "l", 2, 8), ("cfg5", 3, 36, "q", 2, 6), ("cfg5", 1, 20, "q", 2, 7)])
 def test_group_memetic_kernel(sim, oracle, name, B, pop, mode, steps, variant):
