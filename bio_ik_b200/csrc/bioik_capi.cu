@@ -83,6 +83,7 @@ struct bioik_ctx
     std::vector<EventPair> pending, pool;
     double ms_evolve = 0, ms_serial = 0;
     int64_t n_evolve = 0, n_serial = 0;
+    bool stale_tips = false; // BIOIK_OPT_REFERENCE_STALE_TIPS
     int memetic_group = -1; // BIOIK_MEMETIC_GROUP: 0 = memetic step inside the thread-per-task serial kernel, 1 = always k_memetic_group, unset = by problem shape
     // query-level buffers of bioik_solve_islands
     double *d_q_gp = nullptr, *d_q_seeds = nullptr, *d_q_sol = nullptr, *d_q_fit = nullptr;
@@ -141,6 +142,7 @@ int ensure_state(bioik_ctx* ctx, int B)
         (size_t)B * 2 * T * 7 * 8,     // tip0
         (size_t)B * 2 * T * n * 7 * 8, // delta
         (size_t)B * 4,                 // qstep
+        (size_t)B * T * 7 * 8,         // carry
     };
     size_t total = 0;
     for(size_t s : sizes) total += align_up(s);
@@ -167,6 +169,7 @@ int ensure_state(bioik_ctx* ctx, int B)
     S.tip0 = (double*)take(sizes[12]);
     S.delta = (double*)take(sizes[13]);
     S.qstep = (int32_t*)take(sizes[14]);
+    S.carry = (double*)take(sizes[15]);
     ctx->capB = B;
     return BIOIK_OK;
 }
@@ -305,6 +308,7 @@ DState slice_state(const DState& S, const DProblem& P, int q0, int nq)
     H.base += q * 2 * n;
     H.tip0 += q * 2 * T * 7;
     H.delta += q * 2 * T * n * 7;
+    H.carry += q * T * 7;
     H.qstep += q; // only meaningful without islands (enqueue_solve does not slice island batches)
     return H;
 }
@@ -391,14 +395,18 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
             CU(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
         }
         const int MW = memetic_group_width(P.n);
-        const MemeticGroupKernel mgk = select_memetic_group(MW);
+        // reference-quirk mode: the group kernel with one group per QUERY (the two species share the solver's phenotypes3)
+        const bool stale = ctx->stale_tips && S.memetic && stale_tips_matter(P);
+        const MemeticGroupKernel mgk = select_memetic_group(MW, stale);
         const int mg_warps = 4, mg_tasks_per_block = mg_warps * (32 / MW);
         const GroupLayout mgl{P.n, P.T, P.G, MW};
         const size_t mg_smem = (size_t)mg_tasks_per_block * mgl.total() * sizeof(double);
         // the unrolled single-pose path of k_serial issues ~3x fewer instructions per task than a lane group; everything else
         // gains from the extra parallelism of the group kernel
-        const bool want_mg = ctx->memetic_group < 0 ? !has_unrolled_memetic(P) : ctx->memetic_group != 0;
+        const bool want_mg = stale || (ctx->memetic_group < 0 ? !has_unrolled_memetic(P) : ctx->memetic_group != 0);
         const bool use_mg = want_mg && S.memetic && mg_smem <= 200 * 1024;
+        if(stale && !use_mg) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS: problem too large for the lane-group memetic kernel");
+        if(stale && H == 2) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS cannot be combined with BIOIK_PIPELINE");
         if(use_mg && mg_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)mgk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
         auto launch_serial = [&](int h, int step, int phases) -> int {
             const int sgrid = (2 * Sh[h].B + pl.block - 1) / pl.block;
@@ -406,7 +414,8 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
             {
                 // the memetic line search on W lanes per task (bioik_memetic_group.cuh), then the rest of the serial work
                 Timed tg(ctx, ss, 2);
-                mgk<<<(2 * Sh[h].B + mg_tasks_per_block - 1) / mg_tasks_per_block, mg_warps * 32, mg_smem, ss>>>(ctx->hP, Sh[h], step);
+                const int mg_units = stale ? Sh[h].B : 2 * Sh[h].B; // groups own queries in the reference-quirk mode
+                mgk<<<(mg_units + mg_tasks_per_block - 1) / mg_tasks_per_block, mg_warps * 32, mg_smem, ss>>>(ctx->hP, Sh[h], step);
                 int r = check_launch(ctx, "k_memetic_group");
                 tg.done();
                 if(r != BIOIK_OK) return r;
@@ -726,6 +735,20 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_osteps, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return BIOIK_OK;
+}
+
+int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    switch(option)
+    {
+    case BIOIK_OPT_REFERENCE_STALE_TIPS:
+        ctx->stale_tips = value != 0;
+        if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+        ctx->graph_B = -1;
+        return BIOIK_OK;
+    default: return fail(ctx, BIOIK_E_INVALID, "unknown option");
+    }
 }
 
 int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap, double* out_solutions,

@@ -37,6 +37,7 @@ struct DState
     int32_t* steps;    // [B] step() calls executed
     int32_t* success;  // [B]
     int32_t* ccount;   // [B][2][gens] pre-selection child_count (only with secondary goals)
+    double* carry;     // [B][T][7] reference-quirk mode: frames left in the solver's phenotypes3 (identity at the start)
     int32_t* qstep;    // [B / islands] step count at which the first island of the query passed the success test (INT32_MAX: none yet)
     // approximator of the current step
     double* base;  // [B][2][n]
@@ -115,6 +116,8 @@ __global__ void k_init(const DProblem* __restrict__ Pp, DState S)
     draw_preselect_counts(P, S, q, r);
     S.rng[q] = r;
     S.done[q] = 0;
+    for(int t = 0; t < P.T; t++)
+        for(int k = 0; k < 7; k++) S.carry[((size_t)q * P.T + t) * 7 + k] = k == 6 ? 1.0 : 0.0;
     S.qstep[q] = 0x7fffffff;
     S.steps[q] = 0;
     S.success[q] = 0;

@@ -46,31 +46,59 @@ struct GroupLayout
     __host__ __device__ int o_delta() const { return o_pl() + W * 7 * T; }
     __host__ __device__ int o_gp() const { return o_delta() + 7 * T * n; }
     __host__ __device__ int o_sc() const { return o_gp() + GOAL_NPARAM * G; }
-    __host__ __device__ int total() const { return (o_sc() + 8) | 1; } // odd stride: the groups of a warp start in different banks
+    __host__ __device__ int o_carry() const { return o_sc() + 8; }               // [7T] reference-quirk mode: the frames left in phenotypes3
+    __host__ __device__ int o_prev() const { return o_carry() + 7 * T; }          // [T][n] int32: last earlier gene that moves tip t (-1: none)
+    __host__ __device__ int total() const { return (o_prev() + (T * n + 1) / 2) | 1; } // odd stride: the groups of a warp start in different banks
 };
 
 inline int memetic_group_width(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : 32); }
 
 // W lanes per task, 32 / W tasks per warp; blockDim.x = 32 * warps (any number of warps, no block-level sync)
-template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
+//
+// STALE = the reference-quirk mode (bioik_set_option BIOIK_OPT_REFERENCE_STALE_TIPS): the reference's
+// computeApproximateMutation1 skips the tips a variable cannot move (forward_kinematics.h:940), so a probe scores those
+// tips on what phenotypes3[0] held before: the frame written by the last earlier probe of the iteration that moves the tip,
+// else the frames of the previous f3 evaluation (:494) - of the previous iteration, of the other species (the solver has ONE
+// phenotypes3 and treats species 0, then species 1), or of the previous step.  Here a group owns a QUERY, runs its two
+// species one after the other and carries those frames in `carry` (HBM between steps; identity frames at the start, which
+// is what the harness of the reference build pre-fills - a fresh reference solver reads uninitialised memory there).
+template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
 {
     extern __shared__ double smem[];
     constexpr int GPW = 32 / W;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int gl = lane % W, gw = lane / W;
-    const int task_raw = (blockIdx.x * warps_per_block + warp_in_block) * GPW + gw;
-    const bool valid = task_raw < 2 * S.B;
-    const int task = valid ? task_raw : 2 * S.B - 1;
-    const int q = task >> 1, slot = task & 1;
-    bool alive = valid && !run_done(S, q, step) && S.memetic;
+    const int unit_raw = (blockIdx.x * warps_per_block + warp_in_block) * GPW + gw; // task (query, slot), or query in STALE mode
+    const int units = STALE ? S.B : 2 * S.B;
+    const bool valid = unit_raw < units;
+    const int unit = valid ? unit_raw : units - 1;
+    const int q = STALE ? unit : (unit >> 1);
+    const bool live = valid && !run_done(S, q, step) && S.memetic;
     const int n = P.n, T = P.T, G = P.G, T7 = 7 * P.T;
 
     const GroupLayout L{n, T, G, W};
     double* Wk = smem + (size_t)(warp_in_block * GPW + gw) * L.total();
     double *ind = Wk + L.o_ind(), *graw = Wk + L.o_graw(), *grad = Wk + L.o_grad(), *ta = Wk + L.o_ta(), *tb = Wk + L.o_tb(), *base = Wk + L.o_base(), *clip = Wk + L.o_clip();
-    double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *gp = Wk + L.o_gp(), *sc = Wk + L.o_sc();
+    double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *gp = Wk + L.o_gp(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry();
+    int32_t* prev = (int32_t*)(Wk + L.o_prev());
     const double* seed = S.seeds + (size_t)q * P.n_vars;
+    if(STALE && live)
+    {
+        for(int c = gl; c < T7; c += W) carry[c] = S.carry[(size_t)q * T7 + c];
+        for(int k = gl; k < T * n; k += W)
+        {
+            const int t = k / n, i = k - t * n;
+            int j = i - 1;
+            while(j >= 0 && !((P.genes[j].tipmask >> t) & 1)) j--;
+            prev[k] = j;
+        }
+    }
+    for(int slot_it = 0; slot_it < (STALE ? 2 : 1); slot_it++)
+    {
+    const int task = STALE ? 2 * q + slot_it : unit;
+    const int slot = task & 1;
+    bool alive = live;
 
     // ---- stage the task ------------------------------------------------------------------------
     if(alive)
@@ -142,6 +170,14 @@ template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PR
                 for(int t = 0; t < T; t++)
                 {
                     const double* D = delta + ((size_t)t * n + i) * 7;
+                    if(STALE && !((P.genes[i].tipmask >> t) & 1))
+                    {
+                        // the tip keeps what the buffer held: the write of the last earlier probe that moves it, else the carried frame
+                        const int j = prev[t * n + i];
+                        const double* Dj = delta + ((size_t)t * n + (j >= 0 ? j : 0)) * 7;
+                        for(int k = 0; k < 7; k++) ph3[7 * t + k] = j >= 0 ? BIOIK_FMA(dp, Dj[k], f2[7 * t + k]) : carry[7 * t + k];
+                        continue;
+                    }
                     for(int k = 0; k < 7; k++) ph3[7 * t + k] = BIOIK_FMA(dp, D[k], f2[7 * t + k]); // :469
                 }
                 const ProbeGenes x{ind, i, ind[i] + dp}; // :468
@@ -181,6 +217,8 @@ template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PR
         // (7) step size and the candidate (:502-506,:525 / :549-554)
         if(alive)
         {
+            if(STALE)
+                for(int c = gl; c < T7; c += W) carry[c] = pl[T7 + c]; // phenotypes3 now holds the frames of the f3 evaluation (:494)
             const double f2v = sc[1], f1 = sc[2], f3 = sc[3];
             if(quad)
             {
@@ -218,11 +256,15 @@ template <int W> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PR
     }
 
     // individuals[0].genes back to the state (gradients are not touched by the memetic step)
-    if(valid && !run_done(S, q, step) && S.memetic)
+    if(live)
     {
         double* og0 = S.genes + ((size_t)task * 2 + 0) * n;
         for(int i = gl; i < n; i += W) og0[i] = ind[i];
     }
+    __syncwarp(); // the next species of the query re-uses the block
+    } // species of the query (STALE), or the single task
+    if(STALE && live)
+        for(int c = gl; c < T7; c += W) S.carry[(size_t)q * T7 + c] = carry[c];
 }
 
 #ifdef BIOIK_HOSTSIM
@@ -231,6 +273,18 @@ typedef void (*MemeticGroupKernel)(const DProblem&, DState, int);
 typedef void (*MemeticGroupKernel)(const DProblem, DState, int);
 #endif
 
-inline MemeticGroupKernel select_memetic_group(int W) { return W == 8 ? (MemeticGroupKernel)k_memetic_group<8> : (W == 16 ? (MemeticGroupKernel)k_memetic_group<16> : (MemeticGroupKernel)k_memetic_group<32>); }
+inline MemeticGroupKernel select_memetic_group(int W, bool stale = false)
+{
+    if(stale) return W == 8 ? (MemeticGroupKernel)k_memetic_group<8, true> : (W == 16 ? (MemeticGroupKernel)k_memetic_group<16, true> : (MemeticGroupKernel)k_memetic_group<32, true>);
+    return W == 8 ? (MemeticGroupKernel)k_memetic_group<8> : (W == 16 ? (MemeticGroupKernel)k_memetic_group<16> : (MemeticGroupKernel)k_memetic_group<32>);
+}
+
+// the reference-quirk mode changes something only if some gene cannot move some tip
+__host__ __device__ inline bool stale_tips_matter(const DProblem& P)
+{
+    for(int i = 0; i < P.n; i++)
+        if((P.genes[i].tipmask & ((1 << P.T) - 1)) != ((1 << P.T) - 1)) return true;
+    return false;
+}
 
 } // namespace bioik

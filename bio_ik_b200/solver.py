@@ -21,7 +21,7 @@ class IKSolver:
     """One solver context on one GPU.  `population` is children.size() of the reference (2 parents +
     child_count, 18 in the reference; BASELINE "pop")."""
 
-    def __init__(self, robot_model, mode="bio2_memetic", population=18, generations=None, memetic_iters=8, random_seed=1, device=0):
+    def __init__(self, robot_model, mode="bio2_memetic", population=18, generations=None, memetic_iters=8, random_seed=1, device=0, reference_stale_tips=False):
         if mode not in MODES:
             raise BioIKError(_abi.E_INVALID, f"class not found {mode}")  # IKFactory::create, src/utils.h:432-437
         self.lib = _abi.load_library()
@@ -37,6 +37,12 @@ class IKSolver:
         rc = self.lib.bioik_create(C.byref(r), C.byref(cfg), C.byref(self._ctx))
         if rc != _abi.OK:
             raise BioIKError(rc, self.lib.bioik_last_error(None).decode())
+        if reference_stale_tips:
+            self.set_option(_abi.OPT_REFERENCE_STALE_TIPS, 1)
+
+    def set_option(self, option, value):
+        """bioik_set_option; OPT_REFERENCE_STALE_TIPS = 1 reproduces quirk Q2 of the reference's memetic step (see include/bioik_b200.h)"""
+        self._check(self.lib.bioik_set_option(self._ctx, int(option), int(value)))
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:

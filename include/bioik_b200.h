@@ -202,6 +202,17 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
                             double* out_species_fitness, double* out_solutions,
                             double* out_fitness);
 
+/* Options of a solver context.
+ * BIOIK_OPT_REFERENCE_STALE_TIPS (default 0): 1 reproduces quirk Q2 of the reference's memetic step on problems where some
+ *   variable cannot move some tip.  RobotFK_Mutator::computeApproximateMutation1 skips such tips
+ *   (src/forward_kinematics.h:940), so the gradient probe (src/ik_evolution_2.cpp:469-470) scores them on whatever
+ *   phenotypes3[0] held before - the write of an earlier probe, or the frames of the last f3 evaluation (:494) of the previous
+ *   iteration / species / step; a fresh reference solver reads uninitialised memory there, this library starts from
+ *   identity frames.  With 0 the probe scores those tips on the unmoved frame (out[t] = in[t], the evident intent).
+ *   Single-chain problems (every variable moves every tip) are unaffected. */
+enum { BIOIK_OPT_REFERENCE_STALE_TIPS = 1 };
+int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value);
+
 /* One MoveIt-style query solved by many differently seeded islands at once, then reduced the way the reference
  * reduces its solver threads:
  *   - run q * islands + k is island k of query q: the query's goal parameters and seed, rng_seeds[q * islands + k];

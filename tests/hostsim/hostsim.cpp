@@ -184,6 +184,10 @@ void hostsim_sincos(int n, const double* x, double* s, double* c)
 static int g_lpt_want = 16;
 void hostsim_set_evolve_lanes(int lpt) { g_lpt_want = lpt; }
 
+// reference-quirk mode of the memetic step (bioik_set_option BIOIK_OPT_REFERENCE_STALE_TIPS) for the next hostsim_solve calls
+static int g_stale = 0;
+void hostsim_set_stale_tips(int on) { g_stale = on; }
+
 // islands per query of the next hostsim_solve calls (0: plain batch), for early_exit == 2
 static int g_islands = 0;
 void hostsim_set_islands(int islands) { g_islands = islands; }
@@ -204,6 +208,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     size_t n = P.n, T = P.T, gens = cfg->generations;
     std::vector<double> genes(B * 4 * n), grads(B * 4 * n), sfit(B * 2), sol(B * n), solfit(B), base(B * 2 * n), tip0(B * 2 * T * 7), delta(B * 2 * T * n * 7);
     std::vector<int32_t> impr(B * 2), done(B), stp(B), succ(B), cc(B * 2 * gens), qstep(B);
+    std::vector<double> carry(B * T * 7);
     std::vector<uint32_t> rng(B);
     std::vector<double> gp_default;
     if(!goal_params)
@@ -219,7 +224,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit, S.islands = g_islands;
     S.goal_params = goal_params, S.seeds = seeds, S.rng_seeds = rng_seeds;
     S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
-    S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
+    S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.carry = carry.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
@@ -243,7 +248,8 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     {
         // production launch sequence of enqueue_solve(): k_evolve_fast + the fused k_serial (32-thread blocks here)
         SerialPlan pl = make_serial_plan(P);
-        const bool group_memetic = use_fast >= 6; // 6 = k_memetic_group + k_serial(SPECIES|PREPARE), the library's default sequence
+        const bool stale = g_stale && S.memetic && stale_tips_matter(P);
+        const bool group_memetic = use_fast >= 6 || stale; // 6 = k_memetic_group + k_serial(SPECIES|PREPARE), the library's default sequence
         if(use_fast >= 2 && use_fast <= 5)
         {
             // forced placement variant of the serial kernel: 2 = all on chip, 3 = frames local, 4 = delta in HBM, 5 = both off chip
@@ -260,9 +266,9 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
             int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
             if(group_memetic && S.memetic)
             {
-                const int MW = use_fast == 6 ? memetic_group_width(P.n) : (use_fast == 7 ? 8 : (use_fast == 8 ? 16 : 32)); // 7..9 force a width
-                MemeticGroupKernel mgk = select_memetic_group(MW);
-                launch_warp((2 * B + 32 / MW - 1) / (32 / MW), [&]() { mgk(P, S, step); });
+                const int MW = use_fast == 7 ? 8 : (use_fast == 8 ? 16 : (use_fast == 9 ? 32 : memetic_group_width(P.n))); // 7..9 force a width
+                MemeticGroupKernel mgk = select_memetic_group(MW, stale);
+                launch_warp(((stale ? B : 2 * B) + 32 / MW - 1) / (32 / MW), [&]() { mgk(P, S, step); });
                 phases &= ~PH_MEMETIC;
             }
             launch_warp(sgrid, [&]() { ks(P, S, step, phases); });

@@ -356,3 +356,35 @@ def test_gpu_equals_the_reference_code_with_contract_math(name, B, pop, steps):
     for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
         assert np.array_equal(got[k], want[k]), k
     assert np.array_equal(res["success"], want["success"]) and np.array_equal(res["solutions"], want["solutions"])
+
+
+@pytest.mark.parametrize("name,B,pop,steps", [("cfg3", 64, 128, 25), ("cfg5", 48, 128, 12), ("cfg3", 32, 18, 25)])
+def test_gpu_reference_stale_tip_mode_equals_the_reference_code(oracle, name, B, pop, steps):
+    """Multi-tip problems in the reference-quirk mode (BIOIK_OPT_REFERENCE_STALE_TIPS): bit-identical to the oracle's emulation
+    of quirk Q2 and - where oracle/_ref is present - to the reference's own code (contract sin / cos, phenotypes3 pre-filled
+    with identity frames by the harness), i.e. all five BASELINE configurations match the reference's code on the GPU."""
+    w = workloads.make(name, ofk(oracle), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop)
+    robot, gp = w.robot, w.goal_params
+    ref = None
+    try:
+        ref = oracle_lib.Reference("strict")
+        robot, gp = ref.effective_robot(w.robot), ref.effective_goal_params(w.robot, w.problem, w.goal_params, B)
+    except (FileNotFoundError, OSError):
+        pass
+    solver = IKSolver(robot, mode="bio2_memetic", population=pop, random_seed=1, device=0, reference_stale_tips=True).initialize(w.problem)
+    got = solver.trace(gp, w.seeds, w.rng_seeds, steps)
+    want = oracle.solve(robot, w.problem, cfg, gp, w.seeds, w.rng_seeds, steps, flags=8)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+        assert np.array_equal(got[k], want[k]), k
+    if ref is not None:
+        ref.contract_math(True)
+        try:
+            r = ref.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+        finally:
+            ref.contract_math(False)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(got[k], r[k]), ("reference", k)
+    # and the default mode differs on these problems (documented deviation Q2)
+    plain = IKSolver(robot, mode="bio2_memetic", population=pop, random_seed=1, device=0).initialize(w.problem).trace(gp, w.seeds, w.rng_seeds, steps)
+    assert not np.array_equal(plain["genes"], got["genes"])

@@ -63,6 +63,21 @@ def test_simulated_kernels_are_bit_identical_to_the_oracle(sim, oracle, name, B,
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("name,B,pop,mode,steps", [("cfg3", 3, 40, "q", 4), ("cfg5", 2, 36, "q", 3), ("cfg3", 2, 20, "l", 3)])
+def test_reference_stale_tip_mode(sim, oracle, name, B, pop, mode, steps):
+    """BIOIK_OPT_REFERENCE_STALE_TIPS: the memetic probe scores the tips a variable cannot move on what the reference's
+    phenotypes3 buffer held (quirk Q2) - one lane group per query, species in order, the carried frames in the state.
+    The oracle's emulation of the same quirk (flags bit 3) is pinned against the reference's own code in test_reference_pin.py."""
+    w = workloads.make(name, lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode)
+    a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, flags=8)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, fast=True, stale_tips=True)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+        assert np.array_equal(a[k], b[k]), k
+    plain = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps)
+    assert not np.array_equal(plain["genes"], a["genes"])  # the quirk really changes multi-tip runs
+
+
 @pytest.mark.parametrize("lanes", [8, 16, 32])
 def test_generation_kernel_lane_groups(sim, oracle, lanes):
     """k_evolve_fast with 8 / 16 / 32 lanes per task (4 / 2 / 1 tasks per warp) on the single-pose problem: an odd task count
