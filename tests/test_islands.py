@@ -149,11 +149,11 @@ def test_islands_oracle_end_to_end(oracle):
 def test_query_level_early_exit(oracle, sim):
     """early_exit = 2: the reference driver's `finished` flag (src/ik_parallel.h:160-186) - once one island has passed the 4-step
     success test, no island of that query starts another burst.  Oracle (lock-step islands) vs the simulated kernels."""
-    Q = 3
+    Q = 2
     w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=5)
-    w.goal_params, w.seeds = w.goal_params[2:5], w.seeds[2:5]
-    cfg = oracle_lib.make_cfg(population=24)
-    islands, steps = 4, 20
+    w.goal_params, w.seeds = w.goal_params[3:5], w.seeds[3:5]
+    cfg = oracle_lib.make_cfg(population=18)
+    islands, steps = 3, 20
     ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=2)
     runs = ref["runs"]
     st = runs["steps"].reshape(Q, islands)
