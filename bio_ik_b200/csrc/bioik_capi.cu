@@ -487,6 +487,8 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         }
     }
     else
+    {
+    if(ctx->stale_tips && S.memetic && stale_tips_matter(P)) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS is not available with BIOIK_FORCE_GENERIC");
     for(int step = 0; step < steps; step++)
     {
         Timed t1(ctx, st, 1);
@@ -506,6 +508,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         k_species<<<qblocks, TPB, 0, st>>>(ctx->dP, S, step);
         if((rc = check_launch(ctx, "k_species")) != BIOIK_OK) return rc;
         t3.done();
+    }
     }
     k_finalize<<<qblocks, TPB, 0, st>>>(ctx->dP, S, d_osol, d_ofit, d_osucc, d_osteps);
     if((rc = check_launch(ctx, "k_finalize")) != BIOIK_OK) return rc;
