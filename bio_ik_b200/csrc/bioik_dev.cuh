@@ -117,6 +117,8 @@ struct DProblem
     double dep_scale[MAX_SLOTS + MAX_GENES];
     int32_t tip_gene_start[MAX_TIPS + 1]; // genes that can move tip t (DGene::tipmask), ascending: tip_gene[tip_gene_start[t] .. tip_gene_start[t + 1])
     int16_t tip_gene[MAX_TIPS * MAX_GENES];
+    int32_t n_quat;               // floating joints among the genes: quat_gene[k] = gene of rot_x, the next three genes are rot_y, rot_z, rot_w (ik_evolution_2.cpp:118-126)
+    int32_t quat_gene[MAX_GENES / 4];
     int32_t wrap_gene[MAX_GENES]; // 1: the plugin's angle wrap applies (revolute variable, robot without mimic joints; kinematics_plugin.cpp:583-584)
 };
 
@@ -344,8 +346,38 @@ template <class AV> BIOIK_HD F7 joint_frame(const DSlot& S, AV vars)
         double v = vars[S.var];
         f.p = V3{S.axis[0] * v, S.axis[1] * v, S.axis[2] * v};
     }
+    else if(S.type == J_FLOATING) // :120-127: translation + normalised quaternion (tf2 normalized(): q * (1 / length))
+    {
+        f.p = V3{vars[S.var + 0], vars[S.var + 1], vars[S.var + 2]};
+        const double x = vars[S.var + 3], y = vars[S.var + 4], z = vars[S.var + 5], w = vars[S.var + 6];
+        const double sc = 1.0 / BIOIK_SQRT(x * x + y * y + z * z + w * w);
+        f.q = Q4{x * sc, y * sc, z * sc, w * sc};
+    }
     return f;
 }
+// the same with variable `which` of the joint moved by `dv` (numeric differentiation, :700-704)
+template <class AV> BIOIK_HD F7 joint_frame_moved(const DSlot& S, AV vars, int which, double dv)
+{
+    double v[7];
+    for(int k = 0; k < 7; k++) v[k] = vars[S.var + k];
+    v[which] = v[which] + dv;
+    F7 f;
+    f.p = V3{v[0], v[1], v[2]};
+    const double sc = 1.0 / BIOIK_SQRT(v[3] * v[3] + v[4] * v[4] + v[5] * v[5] + v[6] * v[6]);
+    f.q = Q4{v[3] * sc, v[4] * sc, v[5] * sc, v[6] * sc};
+    return f;
+}
+
+// include/bio_ik/frame.h:189-209
+BIOIK_HD F7 frame_invert(const F7& a)
+{
+    F7 r;
+    r.q = quat_inv(a.q);
+    r.p = quat_mul_vec(r.q, V3{-a.p.x, -a.p.y, -a.p.z});
+    return r;
+}
+// change(a, b, c) = a * inverse(b) * c, bracketed like concat(a, tmp, c, r)
+BIOIK_HD F7 frame_change(const F7& a, const F7& b, const F7& c) { return concat(concat(a, frame_invert(b)), c); }
 
 // RobotFK_Fast_Base::applyConfiguration, src/forward_kinematics.h:331-354.
 // frames: [L][7] scratch (global frames of the scheduled links).
@@ -368,7 +400,8 @@ template <class AV, class AF> BIOIK_HD void exact_fk(const DProblem& P, AV vars,
 // RobotFK_Jacobian::computeJacobian (src/forward_kinematics.h:600-730) fused with
 // RobotFK_Mutator::initializeMutationApproximator (:802-930) for one (gene, tip):
 // returns the delta frame; *masked = the :919-926 test.
-template <class AF> BIOIK_HD F7 delta_frame(const DProblem& P, AF frames, int gene, int tip, bool& masked)
+// vars: the post-mimic variables the frames were computed from (read only by the numeric branch of floating joints)
+template <class AF, class AV> BIOIK_HD F7 delta_frame(const DProblem& P, AF frames, AV vars, int gene, int tip, bool& masked)
 {
     const DGene& Gn = P.genes[gene];
     F7 tipf = load_frame(frames + 7 * P.tip_slot[tip]);
@@ -397,6 +430,31 @@ template <class AF> BIOIK_HD F7 delta_frame(const DProblem& P, AF frames, int ge
             q = quat_inv(q);
             V3 v = quat_mul_vec(q, V3{S.axis[0], S.axis[1], S.axis[2]}); // :685
             j0 += v.x * scale; j1 += v.y * scale; j2 += v.z * scale;
+        }
+        else if(S.type == J_FLOATING)
+        {
+            // numeric differentiation (:695-726): move this variable by 1e-5, rebuild the link frame, carry the tip along
+            // (change) and take the twist between the two tip frames (frameTwist, include/bio_ik/frame.h:240-259)
+            const double step_size = 0.00001, inv_step_size = 1.0 / step_size;
+            const F7 jf2 = joint_frame_moved(S, vars, Gn.var - S.var, step_size);
+            const F7 o = load_frame(S.origin);
+            const F7 link2 = S.parent >= 0 ? concat(concat(load_frame(frames + 7 * S.parent), o), jf2) : concat(o, jf2);
+            const F7 tip2 = frame_change(link2, lf, tipf);
+            const F7 rel = concat(frame_invert(tipf), tip2); // inverse(a) * b
+            double w = rel.q.w; // Quaternion::getAngle = 2 acos(w), tf2Acos clamps
+            if(w < -1.0) w = -1.0;
+            if(w > 1.0) w = 1.0;
+            double ra = 2.0 * d_acos(w);
+            if(ra > 3.14159265358979323846) ra -= 2 * 3.14159265358979323846;
+            const double s_squared = 1.0 - rel.q.w * rel.q.w; // Quaternion::getAxis
+            V3 ax = V3{1.0, 0.0, 0.0};
+            if(!(s_squared < 10.0 * 2.2204460492503131e-16))
+            {
+                const double sq = BIOIK_SQRT(s_squared);
+                ax = V3{rel.q.x / sq, rel.q.y / sq, rel.q.z / sq};
+            }
+            j0 += rel.p.x * inv_step_size * scale; j1 += rel.p.y * inv_step_size * scale; j2 += rel.p.z * inv_step_size * scale;
+            j3 += ax.x * ra * inv_step_size * scale; j4 += ax.y * ra * inv_step_size * scale; j5 += ax.z * ra * inv_step_size * scale;
         }
     }
     F7 d;
@@ -717,6 +775,13 @@ BIOIK_HD void reproduce_child(const DProblem& P, int child_index, int rate_exp, 
         gene = clampd(gene, Gn.clip_min, Gn.clip_max);
         child_genes[i] = gene;
         if(child_grads) child_grads[i] = mix(parent_gradient, gene - parent_gene, 0.3);
+    }
+    // :320-324 normalizeFast on the quaternion genes of floating joints (include/bio_ik/frame.h:231-238)
+    for(int k = 0; k < P.n_quat; k++)
+    {
+        double* q = child_genes + P.quat_gene[k];
+        const double f = (3.0 - (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])) * 0.5;
+        q[0] = q[0] * f, q[1] = q[1] * f, q[2] = q[2] * f, q[3] = q[3] * f;
     }
 }
 

@@ -883,6 +883,7 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     const int T = P.T;
     if(lanes_per_task) *lanes_per_task = 32;
     if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
+    if(P.n_quat > 0) return nullptr; // quaternion genes are renormalised after the mutation (couples four genes): generic kernel
     const bool J = P.n_joint_goals > 0;
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);
     int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8

@@ -163,7 +163,8 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         DSlot& S = P.slots[s];
         S.parent = R.parent[l] >= 0 ? slot_of_link[R.parent[l]] : -1;
         S.type = R.jtype[l];
-        if(S.type == BIOIK_JOINT_FLOATING || S.type == BIOIK_JOINT_PLANAR) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "floating / planar joints are not supported on the device yet");
+        if(S.type == BIOIK_JOINT_PLANAR) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "planar joints are not supported on the device yet (MoveIt's computeTransform is not restated)");
+        if(S.type == BIOIK_JOINT_FLOATING && R.mimic[l] >= 0) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "mimicking floating joints are not supported");
         S.var = R.first_var[l];
         S.tipmask = 0;
         for(int k = 0; k < 7; k++) S.origin[k] = R.origin[7 * l + k];
@@ -238,6 +239,19 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
                 ndep++;
                 Gn.dep_count++;
             }
+    }
+    {
+        // quaternion genes of floating joints (src/ik_evolution_2.cpp:118-126): the gene of rot_x; reproduce() normalises the four
+        // doubles starting there, so the joint's rotation variables must be consecutive genes
+        P.n_quat = 0;
+        for(int i = 0; i < p->n_active; i++)
+        {
+            const int v = p->active_vars[i], j = R.var_joint[v];
+            if(j < 0 || R.jtype[j] != BIOIK_JOINT_FLOATING || R.first_var[j] + 3 != v) continue;
+            for(int k = 1; k < 4; k++)
+                if(i + k >= p->n_active || p->active_vars[i + k] != v + k) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "the rotation variables of a floating joint must be consecutive active variables");
+            P.quat_gene[P.n_quat++] = i;
+        }
     }
     {
         // per-tip gene lists of the tip-major generation kernel

@@ -145,7 +145,7 @@ __global__ void k_prepare(const DProblem* __restrict__ Pp, DState S, int step)
         for(int i = 0; i < P.n; i++)
         {
             bool masked;
-            F7 d = delta_frame(P, frames, i, t, masked);
+            F7 d = delta_frame(P, frames, (const double*)vars, i, t, masked);
             store_frame(S.delta + (((size_t)task * P.T + t) * P.n + i) * 7, d);
         }
 }
@@ -638,7 +638,7 @@ __global__ void k_approx_batch(const DProblem* __restrict__ Pp, int B, const dou
         for(int i = 0; i < P.n; i++)
         {
             bool masked;
-            F7 d = delta_frame(P, frames, i, t, masked);
+            F7 d = delta_frame(P, frames, (const double*)vars, i, t, masked);
             store_frame(out_delta + (((size_t)b * P.T + t) * P.n + i) * 7, d);
         }
 }
@@ -662,7 +662,7 @@ __global__ void k_approx_fitness(const DProblem* __restrict__ Pp, int B, int M, 
         for(int i = 0; i < n; i++)
         {
             bool masked;
-            store_frame(delta + ((size_t)t * n + i) * 7, delta_frame(P, frames, i, t, masked));
+            store_frame(delta + ((size_t)t * n + i) * 7, delta_frame(P, frames, (const double*)vars, i, t, masked));
         }
     }
     for(int i = 0; i < n; i++) base[i] = vars[P.genes[i].var];

@@ -596,7 +596,7 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
                 if((P.genes[i].tipmask >> t) & 1)
                 {
                     bool masked;
-                    df = delta_frame(P, frames, i, t, masked);
+                    df = delta_frame(P, frames, CSC(vars), i, t, masked);
                 }
                 else // structurally independent pair: the Jacobian column is exactly zero (:609-617), so is the delta frame
                     df = F7{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};

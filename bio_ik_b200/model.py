@@ -25,7 +25,7 @@ class Link:
 
     def __init__(self, name, parent=None, joint_type=_abi.JOINT_FIXED, xyz=(0, 0, 0), rpy=(0, 0, 0), quat=None,
                  axis=(0, 0, 1), lower=0.0, upper=0.0, bounded=True, velocity=1.0, joint_name=None, mimic=None,
-                 mimic_factor=1.0, mimic_offset=0.0):
+                 mimic_factor=1.0, mimic_offset=0.0, var_lower=None, var_upper=None, var_bounded=None):
         self.name = name
         self.parent = parent
         self.joint_type = joint_type
@@ -36,6 +36,8 @@ class Link:
         self.joint_name = joint_name or (name + "_joint")
         self.mimic = mimic  # joint name of the mimicked joint
         self.mimic_factor, self.mimic_offset = float(mimic_factor), float(mimic_offset)
+        # per-variable bounds of multi-variable joints (floating: 7, planar: 3); None = the MoveIt defaults
+        self.var_lower, self.var_upper, self.var_bounded = var_lower, var_upper, var_bounded
 
 
 class RobotModel:
@@ -79,14 +81,14 @@ class RobotModel:
             if cnt == 1:
                 vmin.append(l.lower), vmax.append(l.upper), vb.append(int(l.bounded)), vv.append(l.velocity)
             elif cnt == 7:  # MoveIt FloatingJointModel defaults
-                vmin += [-1e308] * 3 + [-1.0] * 4
-                vmax += [1e308] * 3 + [1.0] * 4
-                vb += [0] * 3 + [1] * 4
+                vmin += list(l.var_lower) if l.var_lower is not None else [-1e308] * 3 + [-1.0] * 4
+                vmax += list(l.var_upper) if l.var_upper is not None else [1e308] * 3 + [1.0] * 4
+                vb += list(l.var_bounded) if l.var_bounded is not None else [0] * 3 + [1] * 4
                 vv += [l.velocity] * 7
             elif cnt == 3:
-                vmin += [-1e308, -1e308, -math.pi]
-                vmax += [1e308, 1e308, math.pi]
-                vb += [0, 0, 0]
+                vmin += list(l.var_lower) if l.var_lower is not None else [-1e308, -1e308, -math.pi]
+                vmax += list(l.var_upper) if l.var_upper is not None else [1e308, 1e308, math.pi]
+                vb += list(l.var_bounded) if l.var_bounded is not None else [0, 0, 0]
                 vv += [l.velocity] * 3
         a["var_min"] = np.array(vmin, dtype=np.float64)
         a["var_max"] = np.array(vmax, dtype=np.float64)

@@ -177,3 +177,24 @@ def mimic_gripper_arm():
     rm = RobotModel("mimic_gripper_arm", links)
     groups = {"all": JointModelGroup(rm, "all", ["j1", "j2", "j3", "j4", "finger_a_joint", "finger_b_joint", "finger_b_tip_joint"], ["pad_a", "pad_b"])}
     return rm, groups
+
+
+def floating_base_arm():
+    """A 3-DOF arm on a FLOATING base joint (7 variables: translation + quaternion): the reference's floating branch of
+    getJointFrame (src/forward_kinematics.h:120-127), the numeric-differentiation branch of the Jacobian (:695-726) and the
+    quaternion-gene normalisation of reproduce() (src/ik_evolution_2.cpp:118-126,320-324).  The translation is given finite
+    bounds: with MoveIt's default infinite ones the reference's wipeout draws random(getMin, getMax) = inf * 0."""
+    from ._abi import JOINT_FLOATING
+    links = [
+        Link("world", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("base", "world", JOINT_FLOATING, xyz=(0.1, 0.0, 0.2), rpy=(0.0, 0.1, 0.0), velocity=1.0, joint_name="virtual_joint",
+             var_lower=[-0.6, -0.6, -0.3, -1.0, -1.0, -1.0, -1.0], var_upper=[0.6, 0.6, 0.5, 1.0, 1.0, 1.0, 1.0], var_bounded=[1, 1, 1, 1, 1, 1, 1]),
+        Link("l1", "base", JOINT_REVOLUTE, xyz=(0, 0, 0.25), axis=(0, 0, 1), lower=-2.5, upper=2.5, velocity=2.0, joint_name="j1"),
+        Link("l2", "l1", JOINT_REVOLUTE, xyz=(0.05, 0, 0.2), rpy=(0.2, 0, 0), axis=(0, 1, 0), lower=-1.8, upper=1.8, velocity=2.0, joint_name="j2"),
+        Link("l3", "l2", JOINT_REVOLUTE, xyz=(0.3, 0, 0), axis=(0, 1, 0), lower=-2.2, upper=2.2, velocity=3.0, joint_name="j3"),
+        Link("ee", "l3", JOINT_FIXED, xyz=(0.25, 0, 0), rpy=(0, 0.3, 0), joint_name="ee_joint"),
+        Link("camera", "base", JOINT_FIXED, xyz=(0.1, 0, 0.4), joint_name="camera_joint"),
+    ]
+    rm = RobotModel("floating_base_arm", links)
+    groups = {"all": JointModelGroup(rm, "all", ["virtual_joint", "j1", "j2", "j3"], ["ee", "camera"]), "whole_arm": JointModelGroup(rm, "whole_arm", ["virtual_joint", "j1", "j2", "j3"], ["ee"])}
+    return rm, groups

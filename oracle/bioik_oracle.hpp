@@ -186,6 +186,30 @@ inline void normalizeFast(Quat& q)
     q = Quat(q.x * f, q.y * f, q.z * f, q.w * f);
 }
 
+// include/bio_ik/frame.h:240-259 (frameTwist) with tf2's Quaternion::getAngle / getAxis (Appendix C of SURVEY.md);
+// acos through `acos_fn` (libm in the reference, det_acos under the arithmetic contract).  vel / rot: the KDL::Twist members.
+inline void frameTwist(const Frame& a, const Frame& b, double (*acos_fn)(double), Vec3& vel, Vec3& rot)
+{
+    Frame ia, frame;
+    invert(a, ia);
+    concat(ia, b, frame); // inverse(a) * b
+    vel = frame.pos;
+    double w = frame.rot.w; // getAngle(): 2 * tf2Acos(w), tf2Acos clamps to [-1, 1]
+    if(w < -1.0) w = -1.0;
+    if(w > 1.0) w = 1.0;
+    double ra = 2.0 * acos_fn(w);
+    if(ra > +M_PI) ra -= 2 * M_PI;
+    // getAxis()
+    double s_squared = 1.0 - frame.rot.w * frame.rot.w;
+    Vec3 axis(1.0, 0.0, 0.0);
+    if(!(s_squared < 10.0 * 2.2204460492503131e-16))
+    {
+        double sq = std::sqrt(s_squared);
+        axis = Vec3(frame.rot.x / sq, frame.rot.y / sq, frame.rot.z / sq);
+    }
+    rot = axis * ra;
+}
+
 // src/utils.h:319-333
 inline double mix(double a, double b, double f) { return a * (1.0 - f) + b * f; }
 inline double clamp(double v, double lo, double hi)
@@ -656,7 +680,40 @@ public:
                     }
                     continue;
                 }
-                default: throw std::runtime_error("oracle: numeric Jacobian for floating/planar joints not restated yet (:695-726)");
+                default:
+                {
+                    // :695-726 numeric differentiation (floating joints; planar would take the same route through computeTransform)
+                    const double step_size = 0.00001, inv_step_size = 1.0 / step_size;
+                    size_t ivar2 = ivar;
+                    if(J.mimic >= 0) ivar2 = ivar2 - robot_model->links[var_joint].first_var + J.first_var;
+                    const Frame link_frame_1 = global_frames[joint];
+                    double v0 = variables[ivar2];
+                    variables[ivar2] = v0 + step_size;
+                    Frame joint_frame_2;
+                    getJointFrame(joint, variables.data(), joint_frame_2);
+                    variables[ivar2] = v0;
+                    Frame link_frame_2;
+                    if(J.parent >= 0)
+                        concat(global_frames[J.parent], J.origin, joint_frame_2, link_frame_2);
+                    else
+                        concat(J.origin, joint_frame_2, link_frame_2);
+                    for(size_t itip = 0; itip < tip_count; itip++)
+                    {
+                        if(!tip_dependencies[joint * tip_count + itip]) continue;
+                        const Frame tip_frame_1 = tip_frames[itip];
+                        Frame tip_frame_2;
+                        change(link_frame_2, link_frame_1, tip_frame_1, tip_frame_2);
+                        Vec3 tv, tr;
+                        frameTwist(tip_frame_1, tip_frame_2, opt.libm_sincos ? static_cast<double (*)(double)>(std::acos) : det_acos, tv, tr);
+                        jac(itip * 6 + 0, icol) += tv.x * inv_step_size * scale;
+                        jac(itip * 6 + 1, icol) += tv.y * inv_step_size * scale;
+                        jac(itip * 6 + 2, icol) += tv.z * inv_step_size * scale;
+                        jac(itip * 6 + 3, icol) += tr.x * inv_step_size * scale;
+                        jac(itip * 6 + 4, icol) += tr.y * inv_step_size * scale;
+                        jac(itip * 6 + 5, icol) += tr.z * inv_step_size * scale;
+                    }
+                    continue;
+                }
                 }
             }
         }

@@ -90,13 +90,14 @@ std::shared_ptr<moveit::core::RobotModel> makeRobot(const BioikRobot* r)
         case BIOIK_JOINT_REVOLUTE: j.reset(new RevoluteJointModel()), j->type_ = JointModel::REVOLUTE, j->variable_count_ = 1; break;
         case BIOIK_JOINT_PRISMATIC: j.reset(new PrismaticJointModel()), j->type_ = JointModel::PRISMATIC, j->variable_count_ = 1; break;
         case BIOIK_JOINT_FIXED: j.reset(new FixedJointModel()), j->type_ = JointModel::FIXED, j->variable_count_ = 0; break;
-        default: throw std::runtime_error("ref harness: floating / planar joints are not shimmed");
+        case BIOIK_JOINT_FLOATING: j.reset(new JointModel()), j->type_ = JointModel::FLOATING, j->variable_count_ = 7; break; // handled by the reference itself (forward_kinematics.h:120-127)
+        default: throw std::runtime_error("ref harness: planar joints are not shimmed (MoveIt's computeTransform)");
         }
         j->name_ = "joint" + std::to_string(l);
         j->joint_index_ = l;
         j->first_variable_index_ = r->joint_first_var[l] >= 0 ? r->joint_first_var[l] : 0;
         j->axis_ = Eigen::Vector3d(r->joint_axis[3 * l], r->joint_axis[3 * l + 1], r->joint_axis[3 * l + 2]);
-        if(j->variable_count_) j->variable_names_.push_back("var" + std::to_string(r->joint_first_var[l]));
+        for(size_t k = 0; k < j->variable_count_; k++) j->variable_names_.push_back("var" + std::to_string(r->joint_first_var[l] + (int)k));
         std::unique_ptr<LinkModel> link(new LinkModel());
         link->name_ = "link" + std::to_string(l);
         link->link_index_ = l;
@@ -130,10 +131,10 @@ std::shared_ptr<moveit::core::RobotModel> makeRobot(const BioikRobot* r)
         m->link_ptrs_.push_back(link);
         m->joint_ptrs_.push_back(joint);
         m->link_names_.push_back(link->name_);
-        if(joint->variable_count_)
+        for(size_t k = 0; k < joint->variable_count_; k++)
         {
-            int v = r->joint_first_var[l];
-            m->variable_names_[v] = joint->variable_names_[0];
+            int v = r->joint_first_var[l] + (int)k;
+            m->variable_names_[v] = joint->variable_names_[k];
             m->joint_of_variable_[v] = joint;
             m->bounds_[v].min_position_ = r->var_min[v];
             m->bounds_[v].max_position_ = r->var_max[v];
@@ -236,7 +237,8 @@ ProtoCache& protoCache(const BioikRobot* r, const BioikProblem* problem, const c
     for(int i = 0; i < problem->n_active; i++)
     {
         g_proto.group.variable_names_.push_back(g_proto.model->variable_names_[problem->active_vars[i]]);
-        g_proto.group.active_joints_.push_back(g_proto.model->joint_of_variable_[problem->active_vars[i]]);
+        if(g_proto.group.active_joints_.empty() || g_proto.group.active_joints_.back() != g_proto.model->joint_of_variable_[problem->active_vars[i]]) // one entry per joint (a floating joint owns 7 variables)
+            g_proto.group.active_joints_.push_back(g_proto.model->joint_of_variable_[problem->active_vars[i]]);
     }
     IKParams& params = g_proto.params;
     params.robot_model = g_proto.model;
@@ -422,7 +424,7 @@ int ref_approx_fitness_batch(const BioikRobot* robot, const BioikProblem* proble
         for(int i = 0; i < problem->n_active; i++)
         {
             group.variable_names_.push_back(model->variable_names_[problem->active_vars[i]]);
-            group.active_joints_.push_back(model->joint_of_variable_[problem->active_vars[i]]);
+            if(group.active_joints_.empty() || group.active_joints_.back() != model->joint_of_variable_[problem->active_vars[i]]) group.active_joints_.push_back(model->joint_of_variable_[problem->active_vars[i]]);
         }
         IKParams params;
         params.robot_model = model;

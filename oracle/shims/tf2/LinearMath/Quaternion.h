@@ -51,7 +51,17 @@ public:
         else
             return tf2Acos(dot(q) / s) * tf2Scalar(2.0);
     }
-    tf2Scalar getAngle() const { return tf2Scalar(2.) * tf2Acos(m_floats[3]); }
+    tf2Scalar getAngle() const
+    {
+        if(auto hook = vector3AngleAcosHook()) // same test hook as Vector3::angle: the arithmetic contract's acos (frameTwist of the numeric Jacobian)
+        {
+            tf2Scalar c = m_floats[3];
+            if(c < tf2Scalar(-1)) c = tf2Scalar(-1);
+            if(c > tf2Scalar(1)) c = tf2Scalar(1);
+            return tf2Scalar(2.) * hook(c);
+        }
+        return tf2Scalar(2.) * tf2Acos(m_floats[3]);
+    }
     Vector3 getAxis() const
     {
         tf2Scalar s_squared = tf2Scalar(1.) - m_floats[3] * m_floats[3];

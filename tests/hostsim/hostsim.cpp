@@ -230,11 +230,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
     int evolve_lpt = 32;
     EvolveFastKernel fast = use_fast ? select_evolve_fast(P, S.C, 8, &evolve_lpt, g_lpt_want) : nullptr;
-    if(use_fast && !fast)
-    {
-        g_err = "no fast kernel instantiation for this problem";
-        return BIOIK_E_LIMIT;
-    }
+    // no fast instantiation (e.g. quaternion genes): like the library, the production sequence then runs the generic k_evolve
     std::vector<double> mtab;
     if(fast)
     {
@@ -262,7 +258,10 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         if(steps > 0) launch_warp(sgrid, [&]() { ks(P, S, 0, PH_PREPARE); });
         for(int step = 0; step < steps; step++)
         {
-            launch_warp((2 * B + 32 / evolve_lpt - 1) / (32 / evolve_lpt), [&]() { fast(&P, S, step, mtab.data()); });
+            if(fast)
+                launch_warp((2 * B + 32 / evolve_lpt - 1) / (32 / evolve_lpt), [&]() { fast(&P, S, step, mtab.data()); });
+            else
+                launch_warp(2 * B, [&]() { k_evolve(&P, S, step); });
             int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
             if(group_memetic && S.memetic)
             {

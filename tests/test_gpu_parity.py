@@ -24,7 +24,8 @@ def ofk(oracle):
 # rows a9-a11, a6, a7 of SURVEY.md §8(a): exact FK, Jacobian/approximator, approximate fitness
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("maker,group", [(robots.pr2_like, "all"), (robots.pr2_like, "right_arm"), (robots.snake, "all"), (robots.shadow_like_hand, "hand"),
-                                         (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all"), (robots.mimic_gripper_arm, "all")])
+                                         (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all"), (robots.mimic_gripper_arm, "all"),
+                                         (robots.floating_base_arm, "all")])
 def test_exact_fk_and_delta_frames(oracle, maker, group):
     rm, groups = maker()
     g = groups[group]
@@ -202,9 +203,9 @@ def test_error_paths():
     assert e.value.code == _abi.E_LIMIT
     with pytest.raises(BioIKError):
         IKSolver(rm, mode="bio1")
-    # a floating joint on the chain is refused, not silently mis-solved
-    links = [robots.Link("world", None), robots.Link("base", "world", _abi.JOINT_FLOATING, joint_name="virtual"), robots.Link("arm", "base", _abi.JOINT_REVOLUTE, lower=-1, upper=1, joint_name="j")]
-    rm2 = robots.RobotModel("floating", links)
+    # a planar joint on the chain is refused, not silently mis-solved
+    links = [robots.Link("world", None), robots.Link("base", "world", _abi.JOINT_PLANAR, joint_name="virtual"), robots.Link("arm", "base", _abi.JOINT_REVOLUTE, lower=-1, upper=1, joint_name="j")]
+    rm2 = robots.RobotModel("planar", links)
     g2 = robots.JointModelGroup(rm2, "all", ["virtual", "j"], ["arm"])
     pr2 = Problem().initialize(rm2, g2, [G.PositionGoal("arm")])
     with pytest.raises(BioIKError) as e:
@@ -388,3 +389,47 @@ def test_gpu_reference_stale_tip_mode_equals_the_reference_code(oracle, name, B,
     # and the default mode differs on these problems (documented deviation Q2)
     plain = IKSolver(robot, mode="bio2_memetic", population=pop, random_seed=1, device=0).initialize(w.problem).trace(gp, w.seeds, w.rng_seeds, steps)
     assert not np.array_equal(plain["genes"], got["genes"])
+
+
+def floating_problem(oracle, group, B, seed=1):
+    rm, groups = robots.floating_base_arm()
+    g = groups[group]
+    pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
+    rng = np.random.default_rng(seed)
+    targets = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    tips = oracle.fk(rm, pr, targets)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    for gi, rec in enumerate(pr.goal_list):
+        gp[:, gi, 0:7] = tips[:, rec["tip"], 0:7]
+    return rm, pr, gp, seeds
+
+
+@pytest.mark.parametrize("group,mode,gens", [("whole_arm", "q", 8), ("all", "q", 8), ("all", 0, 16), ("whole_arm", "l", 8)])
+def test_floating_base_joint(oracle, group, mode, gens):
+    """a FLOATING joint on the chain (src/forward_kinematics.h:120-127 joint frame, :695-726 numeric
+    Jacobian through frameTwist, src/ik_evolution_2.cpp:118-126,320-324 quaternion-gene normalisation) - bit-identical to the
+    oracle and, where oracle/_ref is present, to the reference's own code (contract sin / cos / acos; quirk mode for the
+    two-tip problem, where the base moves both tips but the arm joints only one)."""
+    B, pop, steps = 48, 64, 12
+    rm, pr, gp, seeds = floating_problem(oracle, group, B)
+    rs = 1 + np.arange(B, dtype=np.uint32)
+    name = {0: "bio2", "q": "bio2_memetic", "l": "bio2_memetic_l"}[mode]
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=gens)
+    got = IKSolver(rm, mode=name, population=pop, random_seed=1, device=0).initialize(pr).trace(gp, seeds, rs, steps)
+    want = oracle.solve(rm, pr, cfg, gp, seeds, rs, steps)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+        assert np.array_equal(got[k], want[k]), k
+    try:
+        ref = oracle_lib.Reference("strict")
+    except (FileNotFoundError, OSError):
+        return
+    robot, gpe = ref.effective_robot(rm), ref.effective_goal_params(rm, pr, gp, B)
+    got = IKSolver(robot, mode=name, population=pop, random_seed=1, device=0, reference_stale_tips=True).initialize(pr).trace(gpe, seeds, rs, steps)
+    ref.contract_math(True)
+    try:
+        r = ref.solve(rm, pr, cfg, gp, seeds, rs, steps)
+    finally:
+        ref.contract_math(False)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+        assert np.array_equal(got[k], r[k]), ("reference", k)

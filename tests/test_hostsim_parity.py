@@ -78,6 +78,35 @@ def test_reference_stale_tip_mode(sim, oracle, name, B, pop, mode, steps):
     assert not np.array_equal(plain["genes"], a["genes"])  # the quirk really changes multi-tip runs
 
 
+def test_floating_base_joint(sim, oracle):
+    """FLOATING joint on the chain: joint frame, numeric delta frames (frameTwist), quaternion-gene normalisation; the production
+    sequence falls back to the generic generation kernel (no fast instantiation with quaternion genes)"""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.floating_base_arm()
+    g = groups["all"]
+    pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
+    rng = np.random.default_rng(1)
+    B = 3
+    targets = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    tips = oracle.fk(rm, pr, targets)
+    t2, dd = sim.fk(rm, pr, targets, delta=True)
+    d, mask = oracle.approx(rm, pr, targets)
+    d = d.copy()
+    d[mask == 0, 6] = 0.0
+    assert np.array_equal(t2, tips) and np.array_equal(dd, d)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    for gi, rec in enumerate(pr.goal_list):
+        gp[:, gi, 0:7] = tips[:, rec["tip"], 0:7]
+    cfg = oracle_lib.make_cfg(population=20)
+    a = oracle.solve(rm, pr, cfg, gp, seeds, 1 + np.arange(B), 3)
+    for fast in (False, True):
+        b = sim.solve(rm, pr, cfg, gp, seeds, 1 + np.arange(B), 3, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+            assert np.array_equal(a[k], b[k]), (k, fast)
+
+
 @pytest.mark.parametrize("lanes", [8, 16, 32])
 def test_generation_kernel_lane_groups(sim, oracle, lanes):
     """k_evolve_fast with 8 / 16 / 32 lanes per task (4 / 2 / 1 tasks per warp) on the single-pose problem: an odd task count

@@ -236,6 +236,27 @@ def test_mimic_joints_and_prismatic(ref, oracle):
         compare(oracle, ref, rm, pr, cfg, gp, seeds, 11 + np.arange(B, dtype=np.uint32), 6)
 
 
+@pytest.mark.parametrize("group", ["whole_arm", "all"])
+def test_floating_joint(ref, oracle, group):
+    """a FLOATING base joint: the reference's own floating branch of getJointFrame (forward_kinematics.h:120-127), its numeric
+    Jacobian (:695-726, frameTwist) and the quaternion-gene normalisation of reproduce() (ik_evolution_2.cpp:118-126,320-324)"""
+    rm, groups = robots.floating_base_arm()
+    g = groups[group]
+    pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
+    rng = np.random.default_rng(1)
+    B = 12
+    targets = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    tips = oracle.fk(rm, pr, targets, libm=True)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    for gi, rec in enumerate(pr.goal_list):
+        gp[:, gi, 0:7] = tips[:, rec["tip"], 0:7]
+    for mode in MODES:
+        memetic, gens = MODES[mode]
+        for pop in (18, 64):
+            compare(oracle, ref, rm, pr, oracle_lib.make_cfg(population=pop, memetic=memetic, generations=gens), gp, seeds, 1 + np.arange(B, dtype=np.uint32), 6)
+
+
 def test_random_trees(ref, oracle):
     """randomly generated kinematic trees (mixed revolute / prismatic / fixed joints, unbounded variables)"""
     for seed in (1, 2, 3):
