@@ -328,6 +328,41 @@ template <class AS, class AG, class AV> BIOIK_HD void assemble_variables(const D
     for(int m = 0; m < P.n_mimic; m++) vars[P.mimics[m].dest] = vars[P.mimics[m].src] * P.mimics[m].factor + P.mimics[m].offset;
 }
 
+// PLANAR joint (:128-135): MoveIt's computeTransform = Translation3d(x, y, 0) * AngleAxisd(theta, UnitZ()), Eigen's
+// AngleAxis::toRotationMatrix for that axis = [[c, -s, 0], [s, c, 0], [0, 0, (1 - c) + c]], then Frame(Isometry3d)
+// (include/bio_ik/frame.h:74-79) with Eigen's matrix -> quaternion (Shoemake).  Third-party arithmetic restated.
+BIOIK_HD F7 planar_frame(double x, double y, double theta)
+{
+    double s, c;
+    d_sincos(theta, s, c);
+    const double m00 = 0.0 * 0.0 + c, m01 = 0.0 - s, m10 = 0.0 + s, m11 = 0.0 * 0.0 + c, m22 = (1.0 - c) * 1.0 + c;
+    F7 f;
+    f.p = V3{x, y, 0.0};
+    double t = m00 + m11 + m22;
+    if(t > 0.0)
+    {
+        t = BIOIK_SQRT(t + 1.0);
+        const double w = 0.5 * t;
+        t = 0.5 / t;
+        f.q = Q4{(0.0 - 0.0) * t, (0.0 - 0.0) * t, (m10 - m01) * t, w};
+    }
+    else if(m22 > m00)
+    {
+        t = BIOIK_SQRT(m22 - m00 - m11 + 1.0);
+        const double z = 0.5 * t;
+        t = 0.5 / t;
+        f.q = Q4{(0.0 + 0.0) * t, (0.0 + 0.0) * t, z, (m10 - m01) * t};
+    }
+    else
+    {
+        t = BIOIK_SQRT(m00 - m11 - m22 + 1.0);
+        const double xx = 0.5 * t;
+        t = 0.5 / t;
+        f.q = Q4{xx, (m10 + m01) * t, (0.0 + 0.0) * t, (0.0 - 0.0) * t};
+    }
+    return f;
+}
+
 // joint-local frame, src/forward_kinematics.h:78-139
 template <class AV> BIOIK_HD F7 joint_frame(const DSlot& S, AV vars)
 {
@@ -353,14 +388,18 @@ template <class AV> BIOIK_HD F7 joint_frame(const DSlot& S, AV vars)
         const double sc = 1.0 / BIOIK_SQRT(x * x + y * y + z * z + w * w);
         f.q = Q4{x * sc, y * sc, z * sc, w * sc};
     }
+    else if(S.type == J_PLANAR)
+        f = planar_frame(vars[S.var + 0], vars[S.var + 1], vars[S.var + 2]);
     return f;
 }
 // the same with variable `which` of the joint moved by `dv` (numeric differentiation, :700-704)
 template <class AV> BIOIK_HD F7 joint_frame_moved(const DSlot& S, AV vars, int which, double dv)
 {
     double v[7];
-    for(int k = 0; k < 7; k++) v[k] = vars[S.var + k];
+    const int cnt = S.type == J_PLANAR ? 3 : 7;
+    for(int k = 0; k < cnt; k++) v[k] = vars[S.var + k];
     v[which] = v[which] + dv;
+    if(S.type == J_PLANAR) return planar_frame(v[0], v[1], v[2]);
     F7 f;
     f.p = V3{v[0], v[1], v[2]};
     const double sc = 1.0 / BIOIK_SQRT(v[3] * v[3] + v[4] * v[4] + v[5] * v[5] + v[6] * v[6]);
@@ -431,7 +470,7 @@ template <class AF, class AV> BIOIK_HD F7 delta_frame(const DProblem& P, AF fram
             V3 v = quat_mul_vec(q, V3{S.axis[0], S.axis[1], S.axis[2]}); // :685
             j0 += v.x * scale; j1 += v.y * scale; j2 += v.z * scale;
         }
-        else if(S.type == J_FLOATING)
+        else if(S.type == J_FLOATING || S.type == J_PLANAR)
         {
             // numeric differentiation (:695-726): move this variable by 1e-5, rebuild the link frame, carry the tip along
             // (change) and take the twist between the two tip frames (frameTwist, include/bio_ik/frame.h:240-259)

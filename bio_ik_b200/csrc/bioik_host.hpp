@@ -163,8 +163,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         DSlot& S = P.slots[s];
         S.parent = R.parent[l] >= 0 ? slot_of_link[R.parent[l]] : -1;
         S.type = R.jtype[l];
-        if(S.type == BIOIK_JOINT_PLANAR) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "planar joints are not supported on the device yet (MoveIt's computeTransform is not restated)");
-        if(S.type == BIOIK_JOINT_FLOATING && R.mimic[l] >= 0) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "mimicking floating joints are not supported");
+        if((S.type == BIOIK_JOINT_FLOATING || S.type == BIOIK_JOINT_PLANAR) && R.mimic[l] >= 0) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "mimicking floating / planar joints are not supported");
         S.var = R.first_var[l];
         S.tipmask = 0;
         for(int k = 0; k < 7; k++) S.origin[k] = R.origin[7 * l + k];

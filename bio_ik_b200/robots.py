@@ -198,3 +198,23 @@ def floating_base_arm():
     rm = RobotModel("floating_base_arm", links)
     groups = {"all": JointModelGroup(rm, "all", ["virtual_joint", "j1", "j2", "j3"], ["ee", "camera"]), "whole_arm": JointModelGroup(rm, "whole_arm", ["virtual_joint", "j1", "j2", "j3"], ["ee"])}
     return rm, groups
+
+
+def planar_base_arm():
+    """The same 3-DOF arm on a PLANAR base joint (x, y, theta): the default branch of the reference's getJointFrame
+    (src/forward_kinematics.h:128-135, MoveIt's computeTransform + Frame(Isometry3d)) and the numeric Jacobian (:695-726).
+    x and y are given finite bounds for the same reason as in floating_base_arm."""
+    from ._abi import JOINT_PLANAR
+    links = [
+        Link("world", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("base", "world", JOINT_PLANAR, xyz=(0.0, 0.1, 0.05), rpy=(0.0, 0.0, 0.2), velocity=1.0, joint_name="virtual_joint",
+             var_lower=[-1.0, -1.0, -3.0], var_upper=[1.0, 1.0, 3.0], var_bounded=[1, 1, 1]),
+        Link("l1", "base", JOINT_REVOLUTE, xyz=(0, 0, 0.25), axis=(0, 0, 1), lower=-2.5, upper=2.5, velocity=2.0, joint_name="j1"),
+        Link("l2", "l1", JOINT_REVOLUTE, xyz=(0.05, 0, 0.2), rpy=(0.2, 0, 0), axis=(0, 1, 0), lower=-1.8, upper=1.8, velocity=2.0, joint_name="j2"),
+        Link("l3", "l2", JOINT_REVOLUTE, xyz=(0.3, 0, 0), axis=(0, 1, 0), lower=-2.2, upper=2.2, velocity=3.0, joint_name="j3"),
+        Link("ee", "l3", JOINT_FIXED, xyz=(0.25, 0, 0), rpy=(0, 0.3, 0), joint_name="ee_joint"),
+        Link("camera", "base", JOINT_FIXED, xyz=(0.1, 0, 0.4), joint_name="camera_joint"),
+    ]
+    rm = RobotModel("planar_base_arm", links)
+    groups = {"all": JointModelGroup(rm, "all", ["virtual_joint", "j1", "j2", "j3"], ["ee", "camera"]), "whole_arm": JointModelGroup(rm, "whole_arm", ["virtual_joint", "j1", "j2", "j3"], ["ee"])}
+    return rm, groups

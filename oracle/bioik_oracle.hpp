@@ -547,7 +547,49 @@ public:
             frame.rot = normalized(Quat(vv[3], vv[4], vv[5], vv[6]));
             return;
         }
-        default: throw std::runtime_error("oracle: joint type not restated yet (planar)");
+        case PLANAR:
+        {
+            // :128-135: joint_model->computeTransform + Frame(Isometry3d).  MoveIt's PlanarJointModel::computeTransform is
+            // Translation3d(x, y, 0) * AngleAxisd(theta, UnitZ()); Eigen's AngleAxis::toRotationMatrix for that axis gives
+            // [[c, -s, 0], [s, c, 0], [0, 0, (1 - c) + c]], and Frame(Isometry3d) (include/bio_ik/frame.h:74-79) converts with
+            // Eigen's matrix -> quaternion (Shoemake).  Third-party arithmetic restated; sin / cos as for revolute joints.
+            const double* vv = vars + L.first_var;
+            double s, c;
+            if(opt.libm_sincos)
+                s = std::sin(vv[2]), c = std::cos(vv[2]);
+            else
+                det_sincos(vv[2], &s, &c);
+            const double m00 = 0.0 * 0.0 + c, m01 = 0.0 - s, m10 = 0.0 + s, m11 = 0.0 * 0.0 + c, m22 = (1.0 - c) * 1.0 + c;
+            frame.pos = Vec3(vv[0], vv[1], 0.0);
+            double t = m00 + m11 + m22;
+            if(t > 0.0)
+            {
+                t = std::sqrt(t + 1.0);
+                double w = 0.5 * t;
+                t = 0.5 / t;
+                frame.rot = Quat((0.0 - 0.0) * t, (0.0 - 0.0) * t, (m10 - m01) * t, w);
+            }
+            else
+            {
+                // largest diagonal element: m11 > m00 never (equal), m22 > m00 whenever the trace is not positive
+                if(m22 > m00)
+                {
+                    t = std::sqrt(m22 - m00 - m11 + 1.0);
+                    double z = 0.5 * t;
+                    t = 0.5 / t;
+                    frame.rot = Quat((0.0 + 0.0) * t, (0.0 + 0.0) * t, z, (m10 - m01) * t);
+                }
+                else
+                {
+                    t = std::sqrt(m00 - m11 - m22 + 1.0);
+                    double x = 0.5 * t;
+                    t = 0.5 / t;
+                    frame.rot = Quat(x, (m10 + m01) * t, (0.0 + 0.0) * t, (0.0 - 0.0) * t);
+                }
+            }
+            return;
+        }
+        default: throw std::runtime_error("oracle: unknown joint type");
         }
     }
 

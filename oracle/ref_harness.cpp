@@ -91,7 +91,8 @@ std::shared_ptr<moveit::core::RobotModel> makeRobot(const BioikRobot* r)
         case BIOIK_JOINT_PRISMATIC: j.reset(new PrismaticJointModel()), j->type_ = JointModel::PRISMATIC, j->variable_count_ = 1; break;
         case BIOIK_JOINT_FIXED: j.reset(new FixedJointModel()), j->type_ = JointModel::FIXED, j->variable_count_ = 0; break;
         case BIOIK_JOINT_FLOATING: j.reset(new JointModel()), j->type_ = JointModel::FLOATING, j->variable_count_ = 7; break; // handled by the reference itself (forward_kinematics.h:120-127)
-        default: throw std::runtime_error("ref harness: planar joints are not shimmed (MoveIt's computeTransform)");
+        case BIOIK_JOINT_PLANAR: j.reset(new JointModel()), j->type_ = JointModel::PLANAR, j->variable_count_ = 3; break; // through the shim's computeTransform (forward_kinematics.h:128-135)
+        default: throw std::runtime_error("ref harness: unknown joint type");
         }
         j->name_ = "joint" + std::to_string(l);
         j->joint_index_ = l;
@@ -324,6 +325,7 @@ void ref_set_contract_math(int on)
 {
     bio_ik::g_contract_math = on;
     tf2::vector3AngleAcosHook() = on ? &bioik_oracle::det_acos : nullptr;
+    moveit::core::JointModel::planarSinCosHook() = on ? &bioik_oracle::det_sincos : nullptr;
 }
 
 // Same signature as oracle_solve_batch (tables argument unused: the reference owns its static tables).

@@ -1,6 +1,7 @@
 // shim: moveit::core::RobotModel / LinkModel / JointModel / JointModelGroup accessors the bio2 path uses
 // (SURVEY.md Appendix B), over a flattened robot table.  Built by oracle/ref_harness.cpp from a BioikRobot.
 #pragma once
+#include <cmath>
 #include <Eigen/Dense>
 #include <memory>
 #include <string>
@@ -43,8 +44,30 @@ public:
     double getMimicOffset() const { return mimic_offset_; }
     const LinkModel* getChildLinkModel() const { return child_link_; }
     const LinkModel* getParentLinkModel() const { return parent_link_; }
-    // only reached for joint types the shim does not provide (planar): identity
-    void computeTransform(const double*, Eigen::Isometry3d& t) const { t = Eigen::Isometry3d(); }
+    // Reached by the reference for PLANAR joints only (forward_kinematics.h:128-135).  MoveIt's PlanarJointModel::computeTransform is
+    //   transf = Eigen::Isometry3d(Eigen::Translation3d(v[0], v[1], 0.0) * Eigen::AngleAxisd(v[2], Eigen::Vector3d::UnitZ()));
+    // restated here with Eigen's AngleAxis::toRotationMatrix arithmetic for the axis (0, 0, 1): third-party behaviour, see README.md.
+    // sincos hook: libm by default, the arithmetic contract's det_sincos when ref_set_contract_math(1) is active.
+    static void (*&planarSinCosHook())(double, double*, double*)
+    {
+        static void (*hook)(double, double*, double*) = nullptr;
+        return hook;
+    }
+    void computeTransform(const double* v, Eigen::Isometry3d& t) const
+    {
+        t = Eigen::Isometry3d();
+        if(type_ != PLANAR) return;
+        double s, c;
+        if(auto hook = planarSinCosHook())
+            hook(v[2], &s, &c);
+        else
+            s = std::sin(v[2]), c = std::cos(v[2]);
+        const double one_minus_c = 1.0 - c; // cos1_axis = (1 - c) * axis
+        t.R(0, 0) = 0.0 * 0.0 + c, t.R(0, 1) = 0.0 - s, t.R(0, 2) = 0.0 + 0.0;
+        t.R(1, 0) = 0.0 + s, t.R(1, 1) = 0.0 * 0.0 + c, t.R(1, 2) = 0.0 - 0.0;
+        t.R(2, 0) = 0.0 - 0.0, t.R(2, 1) = 0.0 + 0.0, t.R(2, 2) = one_minus_c * 1.0 + c;
+        t.t = Eigen::Vector3d(v[0], v[1], 0.0);
+    }
 };
 class RevoluteJointModel : public JointModel
 {

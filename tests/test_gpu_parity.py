@@ -25,7 +25,7 @@ def ofk(oracle):
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("maker,group", [(robots.pr2_like, "all"), (robots.pr2_like, "right_arm"), (robots.snake, "all"), (robots.shadow_like_hand, "hand"),
                                          (lambda: robots.random_tree(1), "all"), (lambda: robots.random_tree(2, n_joints=12, branch_at=7), "all"), (robots.mimic_gripper_arm, "all"),
-                                         (robots.floating_base_arm, "all")])
+                                         (robots.floating_base_arm, "all"), (robots.planar_base_arm, "all")])
 def test_exact_fk_and_delta_frames(oracle, maker, group):
     rm, groups = maker()
     g = groups[group]
@@ -203,11 +203,13 @@ def test_error_paths():
     assert e.value.code == _abi.E_LIMIT
     with pytest.raises(BioIKError):
         IKSolver(rm, mode="bio1")
-    # a planar joint on the chain is refused, not silently mis-solved
-    links = [robots.Link("world", None), robots.Link("base", "world", _abi.JOINT_PLANAR, joint_name="virtual"), robots.Link("arm", "base", _abi.JOINT_REVOLUTE, lower=-1, upper=1, joint_name="j")]
-    rm2 = robots.RobotModel("planar", links)
+    # a floating joint whose rotation variables are not consecutive genes is refused, not silently mis-solved
+    links = [robots.Link("world", None), robots.Link("base", "world", _abi.JOINT_FLOATING, joint_name="virtual"), robots.Link("arm", "base", _abi.JOINT_REVOLUTE, lower=-1, upper=1, joint_name="j")]
+    rm2 = robots.RobotModel("floating", links)
     g2 = robots.JointModelGroup(rm2, "all", ["virtual", "j"], ["arm"])
     pr2 = Problem().initialize(rm2, g2, [G.PositionGoal("arm")])
+    pr2.active_variables = [0, 1, 2, 3, 7, 4, 5, 6]  # rot_x followed by the arm joint
+    pr2._active = np.array(pr2.active_variables, dtype=np.int32)
     with pytest.raises(BioIKError) as e:
         IKSolver(rm2).initialize(pr2)
     assert e.value.code == _abi.E_UNSUPPORTED_JOINT
@@ -391,8 +393,8 @@ def test_gpu_reference_stale_tip_mode_equals_the_reference_code(oracle, name, B,
     assert not np.array_equal(plain["genes"], got["genes"])
 
 
-def floating_problem(oracle, group, B, seed=1):
-    rm, groups = robots.floating_base_arm()
+def floating_problem(oracle, group, B, seed=1, maker=None):
+    rm, groups = (maker or robots.floating_base_arm)()
     g = groups[group]
     pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
     rng = np.random.default_rng(seed)
@@ -405,14 +407,16 @@ def floating_problem(oracle, group, B, seed=1):
     return rm, pr, gp, seeds
 
 
+@pytest.mark.parametrize("maker", [robots.floating_base_arm, robots.planar_base_arm])
 @pytest.mark.parametrize("group,mode,gens", [("whole_arm", "q", 8), ("all", "q", 8), ("all", 0, 16), ("whole_arm", "l", 8)])
-def test_floating_base_joint(oracle, group, mode, gens):
+def test_floating_and_planar_base_joints(oracle, group, mode, gens, maker):
     """a FLOATING joint on the chain (src/forward_kinematics.h:120-127 joint frame, :695-726 numeric
     Jacobian through frameTwist, src/ik_evolution_2.cpp:118-126,320-324 quaternion-gene normalisation) - bit-identical to the
     oracle and, where oracle/_ref is present, to the reference's own code (contract sin / cos / acos; quirk mode for the
-    two-tip problem, where the base moves both tips but the arm joints only one)."""
-    B, pop, steps = 48, 64, 12
-    rm, pr, gp, seeds = floating_problem(oracle, group, B)
+    two-tip problem, where the base moves both tips but the arm joints only one).  PLANAR joints take the same numeric route;
+    their joint frame is MoveIt's computeTransform + Eigen's matrix -> quaternion, restated (oracle/shims/README.md)."""
+    B, pop, steps = 48, 64 if maker is robots.floating_base_arm else 128, 12
+    rm, pr, gp, seeds = floating_problem(oracle, group, B, maker=maker)
     rs = 1 + np.arange(B, dtype=np.uint32)
     name = {0: "bio2", "q": "bio2_memetic", "l": "bio2_memetic_l"}[mode]
     cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=gens)

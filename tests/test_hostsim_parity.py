@@ -78,12 +78,13 @@ def test_reference_stale_tip_mode(sim, oracle, name, B, pop, mode, steps):
     assert not np.array_equal(plain["genes"], a["genes"])  # the quirk really changes multi-tip runs
 
 
-def test_floating_base_joint(sim, oracle):
+@pytest.mark.parametrize("maker", ["floating_base_arm", "planar_base_arm"])
+def test_floating_and_planar_base_joints(sim, oracle, maker):
     """FLOATING joint on the chain: joint frame, numeric delta frames (frameTwist), quaternion-gene normalisation; the production
     sequence falls back to the generic generation kernel (no fast instantiation with quaternion genes)"""
     from bio_ik_b200 import goals as G, robots
     from bio_ik_b200.problem import Problem
-    rm, groups = robots.floating_base_arm()
+    rm, groups = getattr(robots, maker)()
     g = groups["all"]
     pr = Problem().initialize(rm, g, [G.PoseGoal(t) for t in g.tip_links])
     rng = np.random.default_rng(1)

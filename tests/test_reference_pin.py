@@ -236,8 +236,9 @@ def test_mimic_joints_and_prismatic(ref, oracle):
         compare(oracle, ref, rm, pr, cfg, gp, seeds, 11 + np.arange(B, dtype=np.uint32), 6)
 
 
+@pytest.mark.parametrize("maker", ["floating_base_arm", "planar_base_arm"])
 @pytest.mark.parametrize("group", ["whole_arm", "all"])
-def test_floating_joint(ref, oracle, group):
+def test_floating_and_planar_joints(ref, oracle, group, maker):
     """a FLOATING base joint: the reference's own floating branch of getJointFrame (forward_kinematics.h:120-127), its numeric
     Jacobian (:695-726, frameTwist) and the quaternion-gene normalisation of reproduce() (ik_evolution_2.cpp:118-126,320-324)"""
     rm, groups = robots.floating_base_arm()
