@@ -148,9 +148,10 @@ def cpu_rate(args, w_small, seconds):
     reps = -(-n1 // len(w_small.seeds))
     gp, sd, rs = (np.concatenate([a] * reps)[:n1] for a in (w_small.goal_params, w_small.seeds, w_small.rng_seeds))
     t0 = time.perf_counter()
-    o.solve(w_small.robot, w_small.problem, cfg, gp, sd, rs, args.solver_steps, nthreads=threads)
+    res = o.solve(w_small.robot, w_small.problem, cfg, gp, sd, rs, args.solver_steps, nthreads=threads)
     dt = time.perf_counter() - t0
-    return n1 / dt, threads, kind, f"{n1} queries drawn from the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {threads} threads, {dt:.1f} s"
+    quality = {"success_rate": float(np.mean(res["success"])), "median_fitness": float(np.median(res["fitness"]))}
+    return n1 / dt, threads, kind, f"{n1} queries drawn from the {args.config} batch, {args.solver_steps} steps, pop {args.population}, {threads} threads, {dt:.1f} s", quality
 
 
 def run_reference(args):
@@ -171,7 +172,7 @@ def run_reference(args):
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        fast.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, args.solver_steps, nthreads=threads)
+        res = fast.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, args.solver_steps, nthreads=threads)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -185,6 +186,7 @@ def run_reference(args):
                            + "; each step = bounded sample of the batch"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": f"{sample} queries per step x {args.steps} steps", "host_hw_threads": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "quality": {"success_rate": float(np.mean(res["success"])), "median_fitness": float(np.median(res["fitness"]))},
     }
     print(json.dumps(line), flush=True)
 
@@ -342,8 +344,8 @@ def main():
         wcpu, _ = make_workload(args, None)
         nb = B
         wcpu.goal_params, wcpu.seeds, wcpu.rng_seeds = batches[0][0][:nb], batches[0][1][:nb], batches[0][2][:nb]
-        rate, threads, kind, desc = cpu_rate(args, wcpu, args.cpu_seconds)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc, "host_hw_threads": os.cpu_count()}
+        rate, threads, kind, desc, cpu_quality = cpu_rate(args, wcpu, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc, "host_hw_threads": os.cpu_count(), "quality": cpu_quality}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
