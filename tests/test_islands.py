@@ -153,7 +153,7 @@ def test_query_level_early_exit(oracle, sim):
     w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=5)
     w.goal_params, w.seeds = w.goal_params[3:5], w.seeds[3:5]
     cfg = oracle_lib.make_cfg(population=18)
-    islands, steps = 3, 20
+    islands, steps = 3, 16
     ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=2)
     runs = ref["runs"]
     st = runs["steps"].reshape(Q, islands)
