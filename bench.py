@@ -328,16 +328,28 @@ def main():
     achieved = units_per_launch * bytes_per_unit / (ev_mean_ms * 1e-3) / 1e9 if ev_n else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "evolve_traffic.json")
-    if os.path.exists(tp):
+    headline = args.config == "cfg2" and args.population == 128 and B == 10000  # the shape the committed ncu capture was taken on
+    if os.path.exists(tp) and headline:
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    # the unit that actually binds: FP64 pipe.  Algorithmic flops per individual-evaluation from SURVEY.md §8(d) (FMA = 2), peak =
+    # 148 SMs x 64 FP64 FMA lanes x 2 flop x the SM clock sampled during the run
+    fp64 = None
+    if ev_n and args.config == "cfg2":
+        flops_per_unit = 252.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        peak_tf = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+        ach_tf = units_per_launch * flops_per_unit / (ev_mean_ms * 1e-3) / 1e12
+        fp64 = {"achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "flops_per_unit": flops_per_unit,
+                "peak_source": "148 SMs x 64 FMA lanes x 2 x sampled SM clock (nominal pipe width)"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak if achieved else None), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "kernel": "k_evolve", "kernel_ms_per_launch": ev_mean_ms, "kernel_share_of_step": (ev_ms / total_ms if total_ms else None),
                 "serial_kernels_ms_per_step": ser_ms / max(args.steps, 1), "algorithmic_bytes_per_launch": units_per_launch * bytes_per_unit,
-                "note": "persistent per-task state lives in shared memory/L2, so HBM traffic is tiny by design; the binding unit is the FP64 pipe"}
+                "fp64": fp64,
+                "note": "persistent per-task state lives in shared memory/L2, so HBM traffic is tiny by design; the binding unit is the FP64 pipe (see fp64)"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # the contract asks for it on rank 0 at N=1 only
