@@ -39,6 +39,7 @@ struct bioik_ctx
     cudaStream_t stream = nullptr;
     cudaStream_t stream_evolve = nullptr, stream_serial = nullptr; // internal streams of the two-half pipeline
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_evolve[2] = {nullptr, nullptr}, ev_serial[2] = {nullptr, nullptr};
+    int serial_plan_force = -1;
     int lpt_want = 16; // BIOIK_EVOLVE_LPT: lanes per task of the single-pose generation kernel (8, 16 or 32; measured 7.15 / 6.98 / 7.22 ms per cfg2 pass)
     int ch_cap = 8; // BIOIK_EVOLVE_CH: cap of the register block of k_evolve_fast (experiments)
     bool pipeline = false; // BIOIK_PIPELINE=1 enables the two-half overlap (experimental)
@@ -383,6 +384,14 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         DState Sh[2];
         for(int h = 0; h < H; h++) Sh[h] = slice_state(S, P, q0[h], q0[h + 1] - q0[h]);
         ctx->splan = make_serial_plan(P, 2 * Sh[0].B, ctx->sm_count);
+        if(ctx->serial_plan_force >= 0)
+        {
+            // experiment knob BIOIK_SERIAL_PLAN: bit0 = delta frames in shared memory, bit1 = link frames in shared memory
+            SerialPlan& f = ctx->splan;
+            f.delta_smem = ctx->serial_plan_force & 1, f.frames_smem = (ctx->serial_plan_force >> 1) & 1;
+            f.per_thread = serial_fixed_doubles(P) + (f.delta_smem ? 7 * P.T * P.n : 0) + (f.frames_smem ? 7 * P.L : 0);
+            f.smem_bytes = (size_t)f.per_thread * f.block * sizeof(double);
+        }
         ctx->serial = select_serial(ctx->splan);
         const SerialPlan& pl = ctx->splan;
         if(pl.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
@@ -598,6 +607,8 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         ctx->force_generic = fg && fg[0] == '1';
         const char* ng = getenv("BIOIK_NO_GRAPH");
         ctx->use_graphs = !(ng && ng[0] == '1');
+        const char* spf = getenv("BIOIK_SERIAL_PLAN");
+        if(spf) ctx->serial_plan_force = atoi(spf);
         const char* lp = getenv("BIOIK_EVOLVE_LPT");
         if(lp && atoi(lp) > 0) ctx->lpt_want = atoi(lp);
         const char* ch = getenv("BIOIK_EVOLVE_CH");
