@@ -90,6 +90,9 @@ struct bioik_ctx
     double *d_q_gp = nullptr, *d_q_seeds = nullptr, *d_q_sol = nullptr, *d_q_fit = nullptr;
     int32_t *d_q_succ = nullptr, *d_q_island = nullptr, *d_q_steps = nullptr;
     int queryQ = 0;
+    int32_t* d_cancel = nullptr;          // device flag read by every kernel (run_done); set by bioik_cancel through its own stream
+    int32_t* h_one = nullptr;             // pinned constant 1, the source of that copy
+    cudaStream_t stream_cancel = nullptr; // so that the copy overtakes a running solve
     int32_t* d_flag = nullptr; // "any run still active" (bioik_solve_islands polls it between bursts)
     int32_t* h_flag = nullptr; // pinned host copy
     bool serial_split = false; // BIOIK_SERIAL_SPLIT=1: one launch per phase of the serial kernel (phase timing study)
@@ -334,6 +337,7 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     S.total_steps = steps;
     S.early_exit = early_exit;
     S.islands = islands;
+    S.cancel = ctx->d_cancel;
     if(!d_gp)
     {
         // no per-query parameters: broadcast the defaults of BioikGoal::p
@@ -574,6 +578,11 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     }
     cudaError_t e = cudaSetDevice(cfg->device);
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream_cancel, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaMalloc(&ctx->d_cancel, 4);
+    if(e == cudaSuccess) e = cudaMemset(ctx->d_cancel, 0, 4);
+    if(e == cudaSuccess) e = cudaMallocHost(&ctx->h_one, 4);
+    if(e == cudaSuccess) *ctx->h_one = 1;
     if(e == cudaSuccess)
     {
         int lo = 0, hi = 0;
@@ -634,7 +643,9 @@ void bioik_destroy(bioik_ctx* ctx)
     for(auto& p : ctx->pool) cudaEventDestroy(p.a), cudaEventDestroy(p.b);
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
-    cudaFree(ctx->d_flag);
+    cudaFree(ctx->d_flag), cudaFree(ctx->d_cancel);
+    if(ctx->h_one) cudaFreeHost(ctx->h_one);
+    if(ctx->stream_cancel) cudaStreamDestroy(ctx->stream_cancel);
     if(ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -695,6 +706,7 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
     if(B <= 0 || !seeds || !rng_seeds) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaMemsetAsync(ctx->d_cancel, 0, 4, ctx->stream)); // IKParallel::solve: canceled = false (src/ik_parallel.h:211-212)
     int rc = ensure_staging(ctx, B);
     if(rc != BIOIK_OK) return rc;
     const DProblem& P = ctx->hP;
@@ -751,6 +763,15 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     return BIOIK_OK;
 }
 
+int bioik_cancel(bioik_ctx* ctx)
+{
+    if(!ctx || !ctx->d_cancel) return BIOIK_E_INVALID;
+    // may be called from another thread while a solve is running: touches nothing of the context but this stream
+    if(cudaSetDevice(ctx->cfg.device) != cudaSuccess) return BIOIK_E_CUDA;
+    if(cudaMemcpyAsync(ctx->d_cancel, ctx->h_one, 4, cudaMemcpyHostToDevice, ctx->stream_cancel) != cudaSuccess) return BIOIK_E_CUDA;
+    return BIOIK_OK;
+}
+
 int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value)
 {
     if(!ctx) return BIOIK_E_INVALID;
@@ -772,6 +793,7 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
     if(Q <= 0 || islands <= 0 || !seeds || !rng_seeds || !out_solutions || (int64_t)Q * islands > (int64_t)INT32_MAX / 4) return fail(ctx, BIOIK_E_INVALID, "bad solve_islands arguments");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaMemsetAsync(ctx->d_cancel, 0, 4, ctx->stream));
     const int B = Q * islands;
     int rc = ensure_staging(ctx, B);
     if(rc != BIOIK_OK) return rc;

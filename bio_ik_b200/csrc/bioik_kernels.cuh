@@ -38,6 +38,7 @@ struct DState
     int32_t* success;  // [B]
     int32_t* ccount;   // [B][2][gens] pre-selection child_count (only with secondary goals)
     double* carry;     // [B][T][7] reference-quirk mode: frames left in the solver's phenotypes3 (identity at the start)
+    const volatile int32_t* cancel; // device flag set by bioik_cancel (the reference's `volatile int canceled`, src/ik_base.h:143): every run counts as done
     int32_t* qstep;    // [B / islands] step count at which the first island of the query passed the success test (INT32_MAX: none yet)
     // approximator of the current step
     double* base;  // [B][2][n]
@@ -54,7 +55,7 @@ struct DState
 // the driver's success test at an EARLIER check: IKParallel's `finished` flag (src/ik_parallel.h:160,164,171,180), which
 // makes every other solver thread leave its loop at the next test.  `step` = index of the step() about to run; a success
 // found during launch `step` records qstep = step + 1, so runs of the same launch never see it (deterministic).
-__device__ __forceinline__ bool run_done(const DState& S, int q, int step) { return S.done[q] || (S.early_exit == 2 && S.islands > 1 && S.qstep[q / S.islands] <= step); }
+__device__ __forceinline__ bool run_done(const DState& S, int q, int step) { return S.done[q] || (S.early_exit == 2 && S.islands > 1 && S.qstep[q / S.islands] <= step) || (S.cancel && *S.cancel); }
 __device__ __forceinline__ void note_success(const DState& S, int q, int steps_done)
 {
     if(!S.early_exit) return;

@@ -426,6 +426,7 @@ public:
         BioikProblem p = problem.toABI();
         check(bioik_set_problem(ctx_, &p), "bioik_set_problem");
     }
+    void cancel() { check(bioik_cancel(ctx_), "bioik_cancel"); } // IKBase::canceled; callable from another thread
     // bioik_set_option, e.g. BIOIK_OPT_REFERENCE_STALE_TIPS (quirk Q2 of the reference's memetic step on multi-tip problems)
     void setOption(int32_t option, int32_t value) { check(bioik_set_option(ctx_, option, value), "bioik_set_option"); }
     struct Result

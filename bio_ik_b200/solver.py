@@ -40,6 +40,10 @@ class IKSolver:
         if reference_stale_tips:
             self.set_option(_abi.OPT_REFERENCE_STALE_TIPS, 1)
 
+    def cancel(self):
+        """IKBase::canceled: stop the solve in flight (callable from another thread)"""
+        self._check(self.lib.bioik_cancel(self._ctx))
+
     def set_option(self, option, value):
         """bioik_set_option; OPT_REFERENCE_STALE_TIPS = 1 reproduces quirk Q2 of the reference's memetic step (see include/bioik_b200.h)"""
         self._check(self.lib.bioik_set_option(self._ctx, int(option), int(value)))

@@ -213,6 +213,12 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
 enum { BIOIK_OPT_REFERENCE_STALE_TIPS = 1 };
 int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value);
 
+/* IKBase::canceled (src/ik_base.h:143; set for every solver when the driver finishes or times out, polled in the solver's
+ * loops, src/ik_evolution_2.cpp:355,457): makes every run of the solve that is in flight count as finished from the next
+ * kernel on; the call returns what the runs had reached.  The one entry point that may be called from another thread
+ * while bioik_solve_batch / bioik_solve_islands is running; those calls clear the flag when they start. */
+int bioik_cancel(bioik_ctx* ctx);
+
 /* One MoveIt-style query solved by many differently seeded islands at once, then reduced the way the reference
  * reduces its solver threads:
  *   - run q * islands + k is island k of query q: the query's goal parameters and seed, rng_seeds[q * islands + k];

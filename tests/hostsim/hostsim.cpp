@@ -224,7 +224,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit, S.islands = g_islands;
     S.goal_params = goal_params, S.seeds = seeds, S.rng_seeds = rng_seeds;
     S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
-    S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.carry = carry.data(), S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
+    S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.carry = carry.data(), S.cancel = nullptr, S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;

@@ -437,3 +437,27 @@ def test_floating_and_planar_base_joints(oracle, group, mode, gens, maker):
         ref.contract_math(False)
     for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
         assert np.array_equal(got[k], r[k]), ("reference", k)
+
+
+def test_cancel_from_another_thread(oracle):
+    """bioik_cancel = the reference's `canceled` flag (src/ik_base.h:143, polled at ik_evolution_2.cpp:355,457): a solve in flight
+    stops at the next kernel and returns what it had reached; the next solve starts with the flag cleared."""
+    import threading
+    import time
+    w = workloads.make("cfg2", ofk(oracle), batch=4000)
+    solver = IKSolver(w.robot, mode="bio2_memetic", population=128, random_seed=1, device=0).initialize(w.problem)
+    solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 2)  # sizes the state
+    out = {}
+    t = threading.Thread(target=lambda: out.update(solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 400)))
+    t0 = time.perf_counter()
+    t.start()
+    time.sleep(0.02)
+    solver.cancel()
+    t.join()
+    dt = time.perf_counter() - t0
+    assert out["steps"].max() < 400 and dt < 1.0  # 400 steps of 4000 queries take ~1.5 s uncancelled
+    assert np.isfinite(out["fitness"]).all()
+    # the flag is cleared by the next solve: same result as a fresh solver
+    a = solver.solve_batch(w.goal_params[:64], w.seeds[:64], w.rng_seeds[:64], 5)
+    b = oracle.solve(w.robot, w.problem, oracle_lib.make_cfg(population=128), w.goal_params[:64], w.seeds[:64], w.rng_seeds[:64], 5)
+    assert np.array_equal(a["solutions"], b["solutions"]) and a["steps"].min() == 5
