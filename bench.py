@@ -363,7 +363,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w.name, "batch_per_gpu": B, "population": args.population, "solver_steps": S, "generations": 8 * S, "species": 2, "memetic": "q",
-                   "robot": "PR2-like right arm (synthetic table, no URDF offline)", "l2": "flushed (256 MiB memset) between timed iterations", "parallelism": f"query-sharded x{world}"},
+                   "robot": f"{w.robot.name} (synthetic link table, no URDF offline)", "l2": "flushed (256 MiB memset) between timed iterations", "parallelism": f"query-sharded x{world}"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roofline, "cpu_baseline": cpu,
