@@ -750,29 +750,43 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
             __syncwarp(gmask);
+            // the lane's children four at a time: one broadcast read of every other child's secondary fitness serves four ranks
 #pragma unroll 1
-            for(int k = 0; k < FAST_MAX_CPL; k++)
+            for(int k0 = 0; k0 < FAST_MAX_CPL; k0 += 4)
             {
-                int c = lane + 32 * k;
-                if(c < 2 || c >= C) continue;
-                double mine = s_sf[c];
-                int rank = 0;
+                if(lane + 32 * k0 >= C) break;
+                double mine[4];
+                int rank[4];
+#pragma unroll
+                for(int j = 0; j < 4; j++)
+                {
+                    const int c = lane + 32 * (k0 + j);
+                    mine[j] = (c >= 2 && c < C) ? s_sf[c] : 0.0;
+                    rank[j] = 0;
+                }
                 for(int o = 2; o < C; o++)
                 {
-                    double other = s_sf[o];
-                    rank += (other < mine || (other == mine && o < c)) ? 1 : 0;
+                    const double other = s_sf[o];
+#pragma unroll
+                    for(int j = 0; j < 4; j++) rank[j] += (other < mine[j] || (other == mine[j] && o < lane + 32 * (k0 + j))) ? 1 : 0;
                 }
-                if(2 + rank >= child_count) continue;
-                uint64_t kk = fast_fitness_key(s_fit[c]);
-                uint32_t pk = (uint32_t)(2 + rank) * 512u + (uint32_t)c;
-                if(key_less(kk, pk, k1, q1))
+#pragma unroll
+                for(int j = 0; j < 4; j++)
                 {
-                    k2 = k1; q2 = q1;
-                    k1 = kk; q1 = pk;
-                }
-                else if(key_less(kk, pk, k2, q2))
-                {
-                    k2 = kk; q2 = pk;
+                    const int c = lane + 32 * (k0 + j);
+                    if(c < 2 || c >= C) continue;
+                    if(2 + rank[j] >= child_count) continue;
+                    uint64_t kk = fast_fitness_key(s_fit[c]);
+                    uint32_t pk = (uint32_t)(2 + rank[j]) * 512u + (uint32_t)c;
+                    if(key_less(kk, pk, k1, q1))
+                    {
+                        k2 = k1; q2 = q1;
+                        k1 = kk; q1 = pk;
+                    }
+                    else if(key_less(kk, pk, k2, q2))
+                    {
+                        k2 = kk; q2 = pk;
+                    }
                 }
             }
         }
