@@ -32,19 +32,33 @@ struct EventPair
 };
 } // namespace
 
+// launch plan and progress of the solve in flight (bioik_begin .. bioik_get_solution, or one bioik_solve_* call)
+struct RunPlan
+{
+    bool open = false;     // solve_begin has run
+    bool prepared = false; // the approximator (tip frames, delta frames) of step next_step is in the state
+    int B = 0, next_step = 0;
+    int Q = 0, islands = 0; // bioik_begin: queries x islands (0: plain batch)
+    EvolveFastKernel fast = nullptr;
+    int evolve_lpt = 32; // lanes per task of the generation kernel
+    size_t evolve_smem = 0;
+    MemeticGroupKernel mgk = nullptr;
+    int mg_width = 8, mg_warps = 4;
+    size_t mg_smem = 0;
+    bool use_mg = false, stale = false;
+};
+
 struct bioik_ctx
 {
     BioikSolverCfg cfg;
     HostRobot robot;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream_evolve = nullptr, stream_serial = nullptr; // internal streams of the two-half pipeline
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_evolve[2] = {nullptr, nullptr}, ev_serial[2] = {nullptr, nullptr};
     int serial_plan_force = -1;
     int lpt_want = 16; // BIOIK_EVOLVE_LPT: lanes per task of the single-pose generation kernel (8, 16 or 32; measured 7.15 / 6.98 / 7.22 ms per cfg2 pass)
     int ch_cap = 8; // BIOIK_EVOLVE_CH: cap of the register block of k_evolve_fast (experiments)
-    bool pipeline = false; // BIOIK_PIPELINE=1 enables the two-half overlap (experimental)
     std::string error;
     int64_t launches = 0;
+    RunPlan run;
 
     bool has_problem = false;
     DProblem hP;
@@ -123,9 +137,16 @@ int fail(bioik_ctx* ctx, int code, const std::string& msg)
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+void drop_graph(bioik_ctx* ctx);
+
+// The three ensure_* functions may free and reallocate buffers whose addresses a cached CUDA graph of bioik_solve_batch has
+// baked in: each of them drops that graph before it frees anything.
 int ensure_state(bioik_ctx* ctx, int B)
 {
     if(B <= ctx->capB) return BIOIK_OK;
+    drop_graph(ctx);
+    CU(ctx, cudaDeviceSynchronize());
+    ctx->capB = 0; // a failed allocation below must not leave a stale capacity behind
     if(ctx->state_block) cudaFree(ctx->state_block);
     ctx->state_block = nullptr;
     const DProblem& P = ctx->hP;
@@ -181,8 +202,11 @@ int ensure_state(bioik_ctx* ctx, int B)
 int ensure_staging(bioik_ctx* ctx, int B)
 {
     if(B <= ctx->stageB) return BIOIK_OK;
-    cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps);
+    drop_graph(ctx);
+    CU(ctx, cudaDeviceSynchronize());
     ctx->stageB = 0;
+    cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps);
+    ctx->d_gp = ctx->d_seeds = ctx->d_osol = ctx->d_ofit = nullptr, ctx->d_rs = nullptr, ctx->d_osucc = ctx->d_osteps = nullptr;
     const DProblem& P = ctx->hP;
     CU(ctx, cudaMalloc(&ctx->d_gp, (size_t)B * P.G * GOAL_NPARAM * 8));
     CU(ctx, cudaMalloc(&ctx->d_seeds, (size_t)B * P.n_vars * 8));
@@ -197,13 +221,21 @@ int ensure_staging(bioik_ctx* ctx, int B)
 
 int check_launch(bioik_ctx* ctx, const char* what);
 
+void drop_graph(bioik_ctx* ctx)
+{
+    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+    ctx->graph_B = -1;
+}
+
 int ensure_schedules(bioik_ctx* ctx, int steps)
 {
     if(ctx->sched_steps >= steps && ctx->sched_n == ctx->hP.n) return BIOIK_OK;
+    if(ctx->sched_n == ctx->hP.n && ctx->sched_steps > 0) steps = std::max(steps, 2 * ctx->sched_steps); // a resumable solve grows its schedule geometrically
     std::vector<int32_t> go;
     std::vector<uint8_t> re;
     make_schedules(steps, ctx->cfg.generations, ctx->cfg.population, ctx->hP.n, go, re);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    drop_graph(ctx);
+    CU(ctx, cudaDeviceSynchronize()); // kernels of a solve in flight (on any stream) may still read the old tables
     cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab);
     ctx->d_gauss_off = nullptr, ctx->d_rate_exp = nullptr, ctx->d_mtab = nullptr;
     CU(ctx, cudaMalloc(&ctx->d_gauss_off, go.size() * 4));
@@ -289,52 +321,27 @@ __global__ void k_broadcast(const double* __restrict__ src, int per, int B, doub
     if(i < (size_t)B * per) dst[i] = src[i % per];
 }
 
-// view of queries [q0, q0 + nq) of a batch state
-DState slice_state(const DState& S, const DProblem& P, int q0, int nq)
-{
-    DState H = S;
-    const size_t q = (size_t)q0, n = P.n, T = P.T, G = P.G;
-    H.B = nq;
-    H.goal_params += q * G * GOAL_NPARAM;
-    H.seeds += q * P.n_vars;
-    H.rng_seeds += q;
-    H.genes += q * 4 * n;
-    H.grads += q * 4 * n;
-    H.sfit += q * 2;
-    H.impr += q * 2;
-    H.sol += q * n;
-    H.solfit += q;
-    H.rng += q;
-    H.done += q;
-    H.steps += q;
-    H.success += q;
-    H.ccount += q * 2 * S.gens;
-    H.base += q * 2 * n;
-    H.tip0 += q * 2 * T * 7;
-    H.delta += q * 2 * T * n * 7;
-    H.carry += q * T * 7;
-    H.qstep += q; // only meaningful without islands (enqueue_solve does not slice island batches)
-    return H;
-}
+// ---- a solve in three parts: begin (IKBase::initialize for every run), steps [s0, s1) (IKBase::step), finish (getSolution) --------
+// bioik_solve_batch* enqueue all three on one stream; bioik_begin / bioik_step / bioik_get_solution expose them one by one.
 
-// enqueue a whole solve on `st`; all pointers are device pointers
-int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps,
-                  int islands = 0, bool poll = false)
+// IKEvolution2::initialize for B runs + the approximator of step 0.  All pointers are device pointers.
+int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int total_steps, int early_exit, int islands)
 {
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
-    if(B <= 0 || steps < 0 || !d_seeds || !d_rs) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
+    if(B <= 0 || total_steps < 0 || !d_seeds || !d_rs) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
     int rc;
+    ctx->run.open = false;
     if(ctx->pending.size() > 4096) drain_events(ctx); // bound the timing-event backlog
     if((rc = ensure_state(ctx, B)) != BIOIK_OK) return rc;
-    if((rc = ensure_schedules(ctx, std::max(steps, 1))) != BIOIK_OK) return rc;
+    if((rc = ensure_schedules(ctx, std::max(std::min(total_steps, 64), 1))) != BIOIK_OK) return rc;
     const DProblem& P = ctx->hP;
-    DState S = ctx->S;
+    DState& S = ctx->S;
     S.B = B;
     S.C = ctx->cfg.population;
     S.gens = ctx->cfg.generations;
     S.memetic = ctx->cfg.memetic;
     S.memetic_iters = ctx->cfg.memetic_iters;
-    S.total_steps = steps;
+    S.total_steps = total_steps;
     S.early_exit = early_exit;
     S.islands = islands;
     S.cancel = ctx->d_cancel;
@@ -352,42 +359,34 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
     S.rng_seeds = d_rs;
     S.uniform = ctx->d_uniform;
     S.gauss = ctx->d_gauss;
-    S.gauss_off = ctx->d_gauss_off;
-    S.rate_exp = ctx->d_rate_exp;
 
-    const int TPB = 128;
-    int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
+    // launch plan of the step kernels
+    RunPlan& R = ctx->run;
+    R = RunPlan();
+    R.B = B;
+    R.next_step = 0;
+    R.evolve_lpt = 32;
+    R.fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &R.evolve_lpt, ctx->lpt_want);
     const int warps_per_block = BIOIK_EVOLVE_WPB;
-    int evolve_lpt = 32; // lanes per task of the generation kernel
-    EvolveFastKernel fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &evolve_lpt, ctx->lpt_want);
-    const int evolve_tpw = 32 / evolve_lpt; // tasks per warp
-    size_t smem;
-    if(fast)
+    if(R.fast)
     {
         FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1};
-        smem = (size_t)warps_per_block * evolve_tpw * L.total() * sizeof(double);
-        if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R.evolve_smem = (size_t)warps_per_block * (32 / R.evolve_lpt) * L.total() * sizeof(double);
+        if(R.evolve_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)R.fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.evolve_smem));
     }
     else
     {
         EvolveSmem L{P.n, P.T, P.G};
-        smem = (size_t)warps_per_block * L.total() * sizeof(double);
-        if(smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        R.evolve_smem = (size_t)warps_per_block * L.total() * sizeof(double);
+        if(R.evolve_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute(k_evolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.evolve_smem));
     }
-    int eblocks = (2 * B + warps_per_block - 1) / warps_per_block;
-
-    k_init<<<qblocks, TPB, 0, st>>>(ctx->dP, S);
+    const int TPB = 128;
+    k_init<<<(B + TPB - 1) / TPB, TPB, 0, st>>>(ctx->dP, S);
     if((rc = check_launch(ctx, "k_init")) != BIOIK_OK) return rc;
     if(!ctx->force_generic)
     {
-        // Production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial.
-        // The batch is cut in two halves that ping-pong between two internal streams, so the latency-bound serial
-        // kernel of one half runs in the shadow of the throughput-bound generation kernel of the other half.
-        const int H = (B >= 2048 && ctx->pipeline && islands <= 1) ? 2 : 1;
-        int q0[3] = {0, H == 2 ? (B / 2) : B, B};
-        DState Sh[2];
-        for(int h = 0; h < H; h++) Sh[h] = slice_state(S, P, q0[h], q0[h + 1] - q0[h]);
-        ctx->splan = make_serial_plan(P, 2 * Sh[0].B, ctx->sm_count);
+        // production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial
+        ctx->splan = make_serial_plan(P, 2 * B, ctx->sm_count);
         if(ctx->serial_plan_force >= 0)
         {
             // experiment knob BIOIK_SERIAL_PLAN: bit0 = delta frames in shared memory, bit1 = link frames in shared memory
@@ -399,133 +398,169 @@ int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, co
         ctx->serial = select_serial(ctx->splan);
         const SerialPlan& pl = ctx->splan;
         if(pl.smem_bytes > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)ctx->serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        cudaStream_t se = st, ss = st;
-        if(H == 2)
-        {
-            se = ctx->stream_evolve, ss = ctx->stream_serial;
-            CU(ctx, cudaEventRecord(ctx->ev_fork, st));
-            CU(ctx, cudaStreamWaitEvent(se, ctx->ev_fork, 0));
-            CU(ctx, cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
-        }
-        const int MW = memetic_group_width(P.n);
+        R.mg_width = memetic_group_width(P.n);
         // reference-quirk mode: the group kernel with one group per QUERY (the two species share the solver's phenotypes3)
-        const bool stale = ctx->stale_tips && S.memetic && stale_tips_matter(P);
-        const MemeticGroupKernel mgk = select_memetic_group(MW, stale);
-        const int mg_warps = 4, mg_tasks_per_block = mg_warps * (32 / MW);
-        const GroupLayout mgl{P.n, P.T, P.G, MW};
-        const size_t mg_smem = (size_t)mg_tasks_per_block * mgl.total() * sizeof(double);
+        R.stale = ctx->stale_tips && S.memetic && stale_tips_matter(P);
+        R.mgk = select_memetic_group(R.mg_width, R.stale);
+        R.mg_warps = 4;
+        const int mg_tasks_per_block = R.mg_warps * (32 / R.mg_width);
+        const GroupLayout mgl{P.n, P.T, P.G, R.mg_width};
+        R.mg_smem = (size_t)mg_tasks_per_block * mgl.total() * sizeof(double);
         // the unrolled single-pose path of k_serial issues ~3x fewer instructions per task than a lane group; everything else
         // gains from the extra parallelism of the group kernel
-        const bool want_mg = stale || (ctx->memetic_group < 0 ? !has_unrolled_memetic(P) : ctx->memetic_group != 0);
-        const bool use_mg = want_mg && S.memetic && mg_smem <= 200 * 1024;
-        if(stale && !use_mg) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS: problem too large for the lane-group memetic kernel");
-        if(stale && H == 2) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS cannot be combined with BIOIK_PIPELINE");
-        if(use_mg && mg_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)mgk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg_smem));
-        auto launch_serial = [&](int h, int step, int phases) -> int {
-            const int sgrid = (2 * Sh[h].B + pl.block - 1) / pl.block;
-            if(use_mg && (phases & PH_MEMETIC))
-            {
-                // the memetic line search on W lanes per task (bioik_memetic_group.cuh), then the rest of the serial work
-                Timed tg(ctx, ss, 2);
-                const int mg_units = stale ? Sh[h].B : 2 * Sh[h].B; // groups own queries in the reference-quirk mode
-                mgk<<<(mg_units + mg_tasks_per_block - 1) / mg_tasks_per_block, mg_warps * 32, mg_smem, ss>>>(ctx->hP, Sh[h], step);
-                int r = check_launch(ctx, "k_memetic_group");
-                tg.done();
-                if(r != BIOIK_OK) return r;
-                phases &= ~PH_MEMETIC;
-            }
-            if(ctx->serial_split && phases != PH_PREPARE)
-            {
-                int r = BIOIK_OK;
-                for(int ph = 0; ph < 3 && r == BIOIK_OK; ph++)
-                {
-                    if(!(phases & (1 << ph))) continue;
-                    Timed tp(ctx, ss, 2 + ph);
-                    ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, 1 << ph);
-                    r = check_launch(ctx, "k_serial");
-                    tp.done();
-                }
-                return r;
-            }
-            Timed tm(ctx, ss, 1);
-            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, ss>>>(ctx->hP, Sh[h], step, phases);
-            int r = check_launch(ctx, "k_serial");
-            tm.done();
-            if(H == 2) cudaEventRecord(ctx->ev_serial[h], ss);
-            return r;
-        };
-        auto launch_evolve = [&](int h, int step) -> int {
-            const int tasks_per_block = warps_per_block * (fast ? evolve_tpw : 1);
-            const int eb = (2 * Sh[h].B + tasks_per_block - 1) / tasks_per_block;
-            if(H == 2) cudaStreamWaitEvent(se, ctx->ev_serial[h], 0);
-            Timed tm(ctx, se, 0);
-            if(fast)
-                fast<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step, ctx->d_mtab);
-            else
-                k_evolve<<<eb, warps_per_block * 32, smem, se>>>(ctx->dP, Sh[h], step);
-            int r = check_launch(ctx, "k_evolve");
-            tm.done();
-            if(H == 2) cudaEventRecord(ctx->ev_evolve[h], se);
-            return r;
-        };
-        if(steps > 0)
-            for(int h = 0; h < H; h++)
-                if((rc = launch_serial(h, 0, PH_PREPARE)) != BIOIK_OK) return rc;
-        for(int step = 0; step < steps; step++)
-            for(int h = 0; h < H; h++)
-            {
-                if((rc = launch_evolve(h, step)) != BIOIK_OK) return rc;
-                if(H == 2) cudaStreamWaitEvent(ss, ctx->ev_evolve[h], 0);
-                const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (step + 1 < steps ? PH_PREPARE : 0);
-                if((rc = launch_serial(h, step, phases)) != BIOIK_OK) return rc;
-                if(poll && H == 1 && (step + 1) % 4 == 0 && step + 1 < steps)
-                {
-                    // latency mode: after each of the driver's 4-step bursts ask the device whether any run is still going
-                    // and stop enqueueing when none is (every kernel would return at once, but 2 launches per step add up)
-                    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, 4, st));
-                    k_any_active<<<(B + 255) / 256, 256, 0, st>>>(S, step + 1, ctx->d_flag);
-                    if((rc = check_launch(ctx, "k_any_active")) != BIOIK_OK) return rc;
-                    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, st));
-                    CU(ctx, cudaStreamSynchronize(st));
-                    if(*ctx->h_flag == 0) step = steps; // leave both loops
-                }
-            }
-        if(H == 2)
+        const bool want_mg = R.stale || (ctx->memetic_group < 0 ? !has_unrolled_memetic(P) : ctx->memetic_group != 0);
+        R.use_mg = want_mg && S.memetic && R.mg_smem <= 200 * 1024;
+        if(R.stale && !R.use_mg) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS: problem too large for the lane-group memetic kernel");
+        if(R.use_mg && R.mg_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)R.mgk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.mg_smem));
+    }
+    else if(ctx->stale_tips && S.memetic && stale_tips_matter(P))
+        return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS is not available with BIOIK_FORCE_GENERIC");
+    R.open = true;
+    R.prepared = false;
+    return BIOIK_OK;
+}
+
+int launch_serial(bioik_ctx* ctx, cudaStream_t st, int step, int phases)
+{
+    const RunPlan& R = ctx->run;
+    const DState& S = ctx->S;
+    const SerialPlan& pl = ctx->splan;
+    const int sgrid = (2 * S.B + pl.block - 1) / pl.block;
+    if(R.use_mg && (phases & PH_MEMETIC))
+    {
+        // the memetic line search on W lanes per task (bioik_memetic_group.cuh), then the rest of the serial work
+        Timed tg(ctx, st, 2);
+        const int mg_tasks_per_block = R.mg_warps * (32 / R.mg_width);
+        const int mg_units = R.stale ? S.B : 2 * S.B; // groups own queries in the reference-quirk mode
+        R.mgk<<<(mg_units + mg_tasks_per_block - 1) / mg_tasks_per_block, R.mg_warps * 32, R.mg_smem, st>>>(ctx->hP, S, step);
+        int r = check_launch(ctx, "k_memetic_group");
+        tg.done();
+        if(r != BIOIK_OK) return r;
+        phases &= ~PH_MEMETIC;
+    }
+    if(ctx->serial_split && phases != PH_PREPARE)
+    {
+        int r = BIOIK_OK;
+        for(int ph = 0; ph < 3 && r == BIOIK_OK; ph++)
         {
-            // join: the caller's stream continues after both halves are done
-            CU(ctx, cudaEventRecord(ctx->ev_join[0], ss));
-            CU(ctx, cudaEventRecord(ctx->ev_join[1], se));
-            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[0], 0));
-            CU(ctx, cudaStreamWaitEvent(st, ctx->ev_join[1], 0));
+            if(!(phases & (1 << ph))) continue;
+            Timed tp(ctx, st, 2 + ph);
+            ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, 1 << ph);
+            r = check_launch(ctx, "k_serial");
+            tp.done();
+        }
+        return r;
+    }
+    Timed tm(ctx, st, 1);
+    ctx->serial<<<sgrid, pl.block, pl.smem_bytes, st>>>(ctx->hP, S, step, phases);
+    int r = check_launch(ctx, "k_serial");
+    tm.done();
+    return r;
+}
+
+// IKEvolution2::step for steps [s0, s1) of every run that is still going.  `last`: s1 is known to be the end of the solve (the
+// approximator of a further step is not prepared).
+int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
+{
+    RunPlan& R = ctx->run;
+    if(!R.open) return fail(ctx, BIOIK_E_INVALID, "no solve in progress (bioik_begin)");
+    if(s1 <= s0) return BIOIK_OK;
+    int rc;
+    if((rc = ensure_schedules(ctx, s1)) != BIOIK_OK) return rc;
+    DState& S = ctx->S;
+    S.gauss_off = ctx->d_gauss_off;
+    S.rate_exp = ctx->d_rate_exp;
+    const DProblem& P = ctx->hP;
+    const int B = S.B, TPB = 128, warps_per_block = BIOIK_EVOLVE_WPB;
+    const int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
+    if(!ctx->force_generic)
+    {
+        if(!R.prepared)
+        {
+            if((rc = launch_serial(ctx, st, s0, PH_PREPARE)) != BIOIK_OK) return rc;
+            R.prepared = true;
+        }
+        for(int step = s0; step < s1; step++)
+        {
+            {
+                const int tasks_per_block = warps_per_block * (R.fast ? 32 / R.evolve_lpt : 1);
+                const int eb = (2 * B + tasks_per_block - 1) / tasks_per_block;
+                Timed tm(ctx, st, 0);
+                if(R.fast)
+                    R.fast<<<eb, warps_per_block * 32, R.evolve_smem, st>>>(ctx->dP, S, step, ctx->d_mtab);
+                else
+                    k_evolve<<<eb, warps_per_block * 32, R.evolve_smem, st>>>(ctx->dP, S, step);
+                rc = check_launch(ctx, "k_evolve");
+                tm.done();
+                if(rc != BIOIK_OK) return rc;
+            }
+            const bool prep = !(last && step + 1 == s1);
+            const int phases = (S.memetic ? PH_MEMETIC : 0) | PH_SPECIES | (prep ? PH_PREPARE : 0);
+            if((rc = launch_serial(ctx, st, step, phases)) != BIOIK_OK) return rc;
+            R.prepared = prep;
         }
     }
     else
     {
-    if(ctx->stale_tips && S.memetic && stale_tips_matter(P)) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS is not available with BIOIK_FORCE_GENERIC");
-    for(int step = 0; step < steps; step++)
-    {
-        Timed t1(ctx, st, 1);
-        k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
-        if((rc = check_launch(ctx, "k_prepare")) != BIOIK_OK) return rc;
-        t1.done();
-        Timed t2(ctx, st, 0);
-        k_evolve<<<eblocks, warps_per_block * 32, smem, st>>>(ctx->dP, S, step);
-        if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
-        t2.done();
-        Timed t3(ctx, st, 1);
-        if(S.memetic)
+        const int eblocks = (2 * B + warps_per_block - 1) / warps_per_block;
+        for(int step = s0; step < s1; step++)
         {
-            k_memetic<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
-            if((rc = check_launch(ctx, "k_memetic")) != BIOIK_OK) return rc;
+            Timed t1(ctx, st, 1);
+            k_prepare<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
+            if((rc = check_launch(ctx, "k_prepare")) != BIOIK_OK) return rc;
+            t1.done();
+            Timed t2(ctx, st, 0);
+            k_evolve<<<eblocks, warps_per_block * 32, R.evolve_smem, st>>>(ctx->dP, S, step);
+            if((rc = check_launch(ctx, "k_evolve")) != BIOIK_OK) return rc;
+            t2.done();
+            Timed t3(ctx, st, 1);
+            if(S.memetic)
+            {
+                k_memetic<<<tblocks, TPB, 0, st>>>(ctx->dP, S, step);
+                if((rc = check_launch(ctx, "k_memetic")) != BIOIK_OK) return rc;
+            }
+            k_species<<<qblocks, TPB, 0, st>>>(ctx->dP, S, step);
+            if((rc = check_launch(ctx, "k_species")) != BIOIK_OK) return rc;
+            t3.done();
         }
-        k_species<<<qblocks, TPB, 0, st>>>(ctx->dP, S, step);
-        if((rc = check_launch(ctx, "k_species")) != BIOIK_OK) return rc;
-        t3.done();
     }
-    }
-    k_finalize<<<qblocks, TPB, 0, st>>>(ctx->dP, S, d_osol, d_ofit, d_osucc, d_osteps);
-    if((rc = check_launch(ctx, "k_finalize")) != BIOIK_OK) return rc;
+    R.next_step = s1;
     return BIOIK_OK;
+}
+
+// number of runs that would execute step `step` (host polling between the driver's 4-step bursts); synchronises `st`
+int count_active(bioik_ctx* ctx, cudaStream_t st, int step, int* out)
+{
+    if(!ctx->d_flag)
+    {
+        CU(ctx, cudaMalloc(&ctx->d_flag, 4));
+        CU(ctx, cudaMallocHost(&ctx->h_flag, 4));
+    }
+    CU(ctx, cudaMemsetAsync(ctx->d_flag, 0, 4, st));
+    k_count_active<<<(ctx->S.B + 255) / 256, 256, 0, st>>>(ctx->S, step, ctx->d_flag);
+    int rc = check_launch(ctx, "k_count_active");
+    if(rc != BIOIK_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    *out = *ctx->h_flag;
+    return BIOIK_OK;
+}
+
+// getSolution() of every run: full variable vector, primary fitness, success test, step count
+int solve_finish(bioik_ctx* ctx, cudaStream_t st, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
+{
+    const int TPB = 128;
+    k_finalize<<<(ctx->S.B + TPB - 1) / TPB, TPB, 0, st>>>(ctx->dP, ctx->S, d_osol, d_ofit, d_osucc, d_osteps);
+    return check_launch(ctx, "k_finalize");
+}
+
+// enqueue a whole solve on `st`; all pointers are device pointers
+int enqueue_solve(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, const double* d_seeds, const uint32_t* d_rs, int steps, int early_exit, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
+{
+    int rc = solve_begin(ctx, st, B, d_gp, d_seeds, d_rs, steps, early_exit, 0);
+    if(rc != BIOIK_OK) return rc;
+    if((rc = solve_steps(ctx, st, 0, steps, true)) != BIOIK_OK) return rc;
+    return solve_finish(ctx, st, d_osol, d_ofit, d_osucc, d_osteps);
 }
 
 void drain_events_impl(bioik_ctx* ctx)
@@ -583,16 +618,6 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     if(e == cudaSuccess) e = cudaMemset(ctx->d_cancel, 0, 4);
     if(e == cudaSuccess) e = cudaMallocHost(&ctx->h_one, 4);
     if(e == cudaSuccess) *ctx->h_one = 1;
-    if(e == cudaSuccess)
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi); // hi = numerically lowest = highest priority
-        e = cudaStreamCreateWithPriority(&ctx->stream_evolve, cudaStreamNonBlocking, lo);
-        if(e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream_serial, cudaStreamNonBlocking, hi);
-        cudaEvent_t* evs[] = {&ctx->ev_fork, &ctx->ev_join[0], &ctx->ev_join[1], &ctx->ev_evolve[0], &ctx->ev_evolve[1], &ctx->ev_serial[0], &ctx->ev_serial[1]};
-        for(auto* pe : evs)
-            if(e == cudaSuccess) e = cudaEventCreateWithFlags(pe, cudaEventDisableTiming);
-    }
     if(e == cudaSuccess) e = cudaMalloc(&ctx->d_uniform, sizeof(double) * 1024 * 1024 * 8);
     if(e == cudaSuccess) e = cudaMalloc(&ctx->d_gauss, sizeof(double) * 1024 * 1024 * 8);
     if(e == cudaSuccess) e = cudaMalloc(&ctx->dP, sizeof(DProblem));
@@ -626,8 +651,6 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         ctx->memetic_group = mg ? (mg[0] == '0' ? 0 : 1) : -1;
         const char* sp = getenv("BIOIK_SERIAL_SPLIT");
         ctx->serial_split = sp && sp[0] == '1';
-        const char* np = getenv("BIOIK_PIPELINE"); // measured slower than the plain sequence on B200 (wave quantisation of the half grids): opt-in
-        ctx->pipeline = np && np[0] == '1';
     }
     *out = ctx;
     return BIOIK_OK;
@@ -649,10 +672,6 @@ void bioik_destroy(bioik_ctx* ctx)
     if(ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
-    if(ctx->stream_evolve) cudaStreamDestroy(ctx->stream_evolve);
-    if(ctx->stream_serial) cudaStreamDestroy(ctx->stream_serial);
-    for(cudaEvent_t ev : {ctx->ev_fork, ctx->ev_join[0], ctx->ev_join[1], ctx->ev_evolve[0], ctx->ev_evolve[1], ctx->ev_serial[0], ctx->ev_serial[1]})
-        if(ev) cudaEventDestroy(ev);
     delete ctx;
 }
 
@@ -684,8 +703,8 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
     ctx->stageB = 0;
     ctx->queryQ = 0;
     ctx->sched_steps = -1;
-    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
-    ctx->graph_B = -1;
+    drop_graph(ctx);
+    ctx->run = RunPlan();
     ctx->has_problem = true;
     return BIOIK_OK;
 }
@@ -696,6 +715,7 @@ int bioik_solve_batch_device(bioik_ctx* ctx, int32_t B, const double* d_goal_par
     if(!ctx) return BIOIK_E_INVALID;
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CU(ctx, cudaMemsetAsync(ctx->d_cancel, 0, 4, st)); // IKParallel::solve: canceled = false at the start of every solve (src/ik_parallel.h:211-212)
     return enqueue_solve(ctx, st, B, d_goal_params, d_seeds, d_rng_seeds, steps, early_exit, d_out_solutions, d_out_fitness, d_out_success, d_out_steps);
 }
 
@@ -750,7 +770,7 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     }
     else
     {
-        if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
+        drop_graph(ctx);
         rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
         if(rc != BIOIK_OK) return rc;
         ctx->graph_B = B, ctx->graph_steps = steps, ctx->graph_early = early_exit, ctx->graph_gp = has_gp;
@@ -779,21 +799,20 @@ int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value)
     {
     case BIOIK_OPT_REFERENCE_STALE_TIPS:
         ctx->stale_tips = value != 0;
-        if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr;
-        ctx->graph_B = -1;
+        drop_graph(ctx);
         return BIOIK_OK;
     default: return fail(ctx, BIOIK_E_INVALID, "unknown option");
     }
 }
 
-int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap, double* out_solutions,
-                        double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+int bioik_begin(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t max_steps, int32_t early_exit)
 {
     if(!ctx) return BIOIK_E_INVALID;
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
-    if(Q <= 0 || islands <= 0 || !seeds || !rng_seeds || !out_solutions || (int64_t)Q * islands > (int64_t)INT32_MAX / 4) return fail(ctx, BIOIK_E_INVALID, "bad solve_islands arguments");
+    if(Q <= 0 || islands <= 0 || max_steps < 0 || !seeds || !rng_seeds || (int64_t)Q * islands > (int64_t)INT32_MAX / 4) return fail(ctx, BIOIK_E_INVALID, "bad bioik_begin arguments");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
-    CU(ctx, cudaMemsetAsync(ctx->d_cancel, 0, 4, ctx->stream));
+    ctx->run.open = false;
+    CU(ctx, cudaMemsetAsync(ctx->d_cancel, 0, 4, ctx->stream)); // IKParallel::solve: canceled = false (src/ik_parallel.h:211-212)
     const int B = Q * islands;
     int rc = ensure_staging(ctx, B);
     if(rc != BIOIK_OK) return rc;
@@ -803,6 +822,7 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
     {
         CU(ctx, cudaStreamSynchronize(st));
         cudaFree(ctx->d_q_gp), cudaFree(ctx->d_q_seeds), cudaFree(ctx->d_q_sol), cudaFree(ctx->d_q_fit), cudaFree(ctx->d_q_succ), cudaFree(ctx->d_q_island), cudaFree(ctx->d_q_steps);
+        ctx->d_q_gp = ctx->d_q_seeds = ctx->d_q_sol = ctx->d_q_fit = nullptr, ctx->d_q_succ = ctx->d_q_island = ctx->d_q_steps = nullptr;
         ctx->queryQ = 0;
         CU(ctx, cudaMalloc(&ctx->d_q_gp, (size_t)Q * P.G * GOAL_NPARAM * 8 + 8));
         CU(ctx, cudaMalloc(&ctx->d_q_seeds, (size_t)Q * P.n_vars * 8));
@@ -822,16 +842,47 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
         k_expand_islands<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, islands, per_gp, per_seed, goal_params ? ctx->d_q_gp : nullptr, ctx->d_q_seeds, ctx->d_gp, ctx->d_seeds);
         if((rc = check_launch(ctx, "k_expand_islands")) != BIOIK_OK) return rc;
     }
-    if(ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec), ctx->graph_exec = nullptr; // the staging buffers are shared with the cached solve_batch graph
-    ctx->graph_B = -1;
-    if(!ctx->d_flag)
-    {
-        CU(ctx, cudaMalloc(&ctx->d_flag, 4));
-        CU(ctx, cudaMallocHost(&ctx->h_flag, 4));
-    }
-    rc = enqueue_solve(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, steps, early_exit, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps, islands, early_exit != 0);
+    drop_graph(ctx); // the staging buffers are shared with the cached solve_batch graph
+    // no step budget: the driver's test still runs after every 4th step, there is just no "last step" (src/ik_parallel.h:165-181)
+    rc = solve_begin(ctx, st, B, goal_params ? ctx->d_gp : nullptr, ctx->d_seeds, ctx->d_rs, max_steps > 0 ? max_steps : INT32_MAX, early_exit, islands);
     if(rc != BIOIK_OK) return rc;
-    // without per-query parameters enqueue_solve has broadcast the defaults into d_gp
+    ctx->run.Q = Q, ctx->run.islands = islands;
+    CU(ctx, cudaStreamSynchronize(st)); // the caller's host buffers are free again
+    return BIOIK_OK;
+}
+
+int bioik_step(bioik_ctx* ctx, int32_t nsteps, int32_t* out_active)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->run.open || ctx->run.islands <= 0) return fail(ctx, BIOIK_E_INVALID, "bioik_step without bioik_begin");
+    if(nsteps < 0) return fail(ctx, BIOIK_E_INVALID, "negative step count");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const int s0 = ctx->run.next_step, total = ctx->S.total_steps;
+    const int s1 = (int)std::min<int64_t>((int64_t)s0 + nsteps, total);
+    int rc = solve_steps(ctx, ctx->stream, s0, s1, s1 == total);
+    if(rc != BIOIK_OK) return rc;
+    if(out_active)
+    {
+        int active = 0;
+        if(s1 < total && (rc = count_active(ctx, ctx->stream, s1, &active)) != BIOIK_OK) return rc;
+        *out_active = active;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return BIOIK_OK;
+}
+
+int bioik_get_solution(bioik_ctx* ctx, int32_t wrap, double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->run.open || ctx->run.islands <= 0) return fail(ctx, BIOIK_E_INVALID, "bioik_get_solution without bioik_begin");
+    if(!out_solutions) return fail(ctx, BIOIK_E_INVALID, "out_solutions is required");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const DProblem& P = ctx->hP;
+    cudaStream_t st = ctx->stream;
+    const int Q = ctx->run.Q, islands = ctx->run.islands;
+    int rc = solve_finish(ctx, st, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps);
+    if(rc != BIOIK_OK) return rc;
+    // (without per-query parameters solve_begin has broadcast the defaults into d_gp)
     k_select_islands<<<(Q + 127) / 128, 128, 0, st>>>(ctx->dP, Q, islands, ctx->d_gp, ctx->d_seeds, ctx->d_osol, ctx->d_ofit, ctx->d_osucc, ctx->d_osteps, wrap, ctx->d_q_sol, ctx->d_q_fit, ctx->d_q_succ, ctx->d_q_island,
                                                       ctx->d_q_steps);
     if((rc = check_launch(ctx, "k_select_islands")) != BIOIK_OK) return rc;
@@ -842,6 +893,25 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
     if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_q_steps, (size_t)Q * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return BIOIK_OK;
+}
+
+int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap, double* out_solutions,
+                        double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!out_solutions || steps < 0) return fail(ctx, BIOIK_E_INVALID, "bad solve_islands arguments");
+    int rc = bioik_begin(ctx, Q, islands, goal_params, seeds, rng_seeds, steps, early_exit);
+    if(rc != BIOIK_OK) return rc;
+    if(steps == 0) ctx->S.total_steps = 0; // bioik_begin reads 0 as "no budget"
+    // the driver's 4-step bursts (src/ik_parallel.h:165-168); with an early exit the host asks after each of them whether any run
+    // is still going and stops enqueueing when none is (every kernel would return at once, but the launches add up)
+    for(int s = 0; s < steps; s += 4)
+    {
+        int32_t active = 1;
+        if((rc = bioik_step(ctx, std::min(4, steps - s), early_exit ? &active : nullptr)) != BIOIK_OK) return rc;
+        if(early_exit && !active) break;
+    }
+    return bioik_get_solution(ctx, wrap, out_solutions, out_fitness, out_success, out_island, out_steps);
 }
 
 int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, double* out_genes, double* out_gradients, double* out_species_fitness,

@@ -183,7 +183,12 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         int m = R.mimic[l];
         if(m >= 0)
         {
-            while(R.mimic[m] >= 0 && R.mimic[m] != l) m = R.mimic[m];
+            int hops = 0;
+            while(R.mimic[m] >= 0 && R.mimic[m] != l)
+            {
+                m = R.mimic[m];
+                if(++hops > R.n_links) return host_fail(err, BIOIK_E_INVALID, "mimic joints form a cycle");
+            }
             deps[m].push_back(l);
         }
     }
@@ -192,6 +197,8 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
     for(int l = 0; l < R.n_links; l++)
         if(R.mimic[l] >= 0)
         {
+            if(P.n_mimic >= MAX_VARS) return host_fail(err, BIOIK_E_LIMIT, "more than 64 mimic joints");
+            if(var_count(R.jtype[l]) < 1 || var_count(R.jtype[R.mimic[l]]) < 1) return host_fail(err, BIOIK_E_INVALID, "a mimic joint and the joint it mimics need a variable each");
             DMimic& M = P.mimics[P.n_mimic++];
             M.dest = R.first_var[l];
             M.src = R.first_var[R.mimic[l]];
@@ -231,7 +238,8 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
             for(int jl : deps[j])
             {
                 double scale = 1;
-                for(int m = jl; R.mimic[m] >= 0 && R.mimic[m] != jl; m = R.mimic[m]) scale *= R.mimic_factor[m];
+                int hops = 0;
+                for(int m = jl; R.mimic[m] >= 0 && R.mimic[m] != jl && hops <= R.n_links; m = R.mimic[m], hops++) scale *= R.mimic_factor[m];
                 P.dep_slot[ndep] = slot_of_link[jl];
                 P.dep_scale[ndep] = scale;
                 Gn.tipmask |= P.slots[slot_of_link[jl]].tipmask;

@@ -559,12 +559,16 @@ __global__ void k_finalize(const DProblem* __restrict__ Pp, DState S, double* ou
 // Many differently seeded islands of ONE query: the batch holds Q x islands runs,
 // run q * islands + k being island k of query q.
 // ---------------------------------------------------------------------------
-// host polling between 4-step bursts: *flag = 1 if any run would still execute step `step`
-__global__ void k_any_active(DState S, int step, int32_t* flag)
+#ifndef BIOIK_HOSTSIM
+// host polling between 4-step bursts: *count = number of runs that would still execute step `step`
+__global__ void k_count_active(DState S, int step, int32_t* count)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if(q < S.B && !run_done(S, q, step)) *flag = 1;
+    const bool on = q < S.B && !run_done(S, q, step);
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
+#endif
 
 // island inputs from query inputs: goal parameters [Q][G][NPARAM] and seeds [Q][n_vars] repeated `islands` times
 __global__ void k_expand_islands(int Q, int islands, int per_gp, int per_seed, const double* gp, const double* seeds, double* gp_out, double* seeds_out)

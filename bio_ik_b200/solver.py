@@ -104,6 +104,31 @@ class IKSolver:
                                                  _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
         return res
 
+    # ---- the reference's solver interface in its resumable form (IKBase::initialize / step / getSolution, src/ik_base.h:138-154)
+    def begin(self, goal_params, seeds, islands=1, rng_seeds=None, max_steps=0, early_exit=0):
+        """initialize(problem) for Q queries x `islands` runs; the state stays on the device until the next begin / solve_*"""
+        rm, pr = self.robot_model, self.problem
+        seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, rm.n_vars)
+        Q = seeds.shape[0]
+        gp = None if goal_params is None else np.ascontiguousarray(goal_params, dtype=np.float64).reshape(Q, pr.n_goals, _abi.GOAL_NPARAM)
+        rs = (1 + np.arange(Q * islands)).astype(np.uint32) if rng_seeds is None else np.ascontiguousarray(rng_seeds, dtype=np.uint32).reshape(Q * islands)
+        self._check(self.lib.bioik_begin(self._ctx, Q, int(islands), _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), int(max_steps), int(early_exit)))
+        self._queries = Q
+        return self
+
+    def step(self, nsteps=1):
+        """step() x nsteps; returns the number of runs that would execute a further step"""
+        active = C.c_int32(0)
+        self._check(self.lib.bioik_step(self._ctx, int(nsteps), C.byref(active)))
+        return active.value
+
+    def get_solution(self, wrap=False):
+        """getSolution() per query after the driver's selection among its runs"""
+        Q, rm = self._queries, self.robot_model
+        res = dict(solutions=np.empty((Q, rm.n_vars)), fitness=np.empty(Q), success=np.empty(Q, dtype=np.int32), island=np.empty(Q, dtype=np.int32), steps=np.empty(Q, dtype=np.int32))
+        self._check(self.lib.bioik_get_solution(self._ctx, int(wrap), _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"])))
+        return res
+
     def solve_batch_device(self, B, d_goal_params, d_seeds, d_rng_seeds, steps, early_exit, d_solutions, d_fitness, d_success, d_steps, stream=None):
         """Same with raw device pointers (ints); enqueues on `stream` (or the context stream), no sync."""
         self._check(self.lib.bioik_solve_batch_device(self._ctx, B, d_goal_params, d_seeds, d_rng_seeds, steps, int(early_exit), d_solutions, d_fitness, d_success, d_steps, stream))

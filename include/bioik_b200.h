@@ -216,7 +216,8 @@ int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value);
 /* IKBase::canceled (src/ik_base.h:143; set for every solver when the driver finishes or times out, polled in the solver's
  * loops, src/ik_evolution_2.cpp:355,457): makes every run of the solve that is in flight count as finished from the next
  * kernel on; the call returns what the runs had reached.  The one entry point that may be called from another thread
- * while bioik_solve_batch / bioik_solve_islands is running; those calls clear the flag when they start. */
+ * while a solve is running; every bioik_solve_* call and bioik_begin clear the flag when they start (IKParallel::solve resets
+ * canceled at the start of each solve, src/ik_parallel.h:211-212). */
 int bioik_cancel(bioik_ctx* ctx);
 
 /* One MoveIt-style query solved by many differently seeded islands at once, then reduced the way the reference
@@ -244,6 +245,35 @@ int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double
                         const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap,
                         double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island,
                         int32_t* out_steps);
+
+/* ---- the resumable form: the reference's solver interface initialize / step / getSolution -----------------------------
+ * IKParallel::solverthread drives a solver through exactly these three calls (src/ik_parallel.h:156,165-181):
+ *   solvers[i]->initialize(problem);  solvers[i]->step() x4;  result = solvers[i]->getSolution();  ... until success/timeout.
+ * bioik_begin / bioik_step / bioik_get_solution are those calls for Q queries x `islands` differently seeded runs each;
+ * the solver state stays resident on the device between the calls, so k calls of bioik_step(ctx, 1) cost the same device
+ * work as one bioik_step(ctx, k).  bioik_solve_islands is begin + step(4) ... + get_solution.
+ * adapter/ik_evolution_2_b200.cpp is the IKBase subclass that forwards to them. */
+
+/* IKBase::initialize(problem) + IKEvolution2::initialize (src/ik_base.h:154-161, src/ik_evolution_2.cpp:111-230) for every
+ * run: copies goal_params [Q][n_goals][BIOIK_GOAL_NPARAM] (or NULL), seeds [Q][n_vars] and rng_seeds [Q * islands] to the
+ * device (the host buffers are free when the call returns) and resets genes, gradients, species, solution and RNG state.
+ * max_steps > 0: a step budget - like bioik_solve_islands the driver's test then also runs after the last step and
+ * bioik_step never goes beyond it; 0: no budget (the reference's wall-clock loop: the caller decides when to stop).
+ * early_exit as in bioik_solve_islands. */
+int bioik_begin(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds,
+                const uint32_t* rng_seeds, int32_t max_steps, int32_t early_exit);
+
+/* IKBase::step() (src/ik_evolution_2.cpp:328-646) `nsteps` times for every run that is still going; returns when the
+ * device has finished them.  out_active (may be NULL) receives the number of runs that would execute a further step
+ * (0 once every run has finished through its early exit, the budget or bioik_cancel). */
+int bioik_step(bioik_ctx* ctx, int32_t nsteps, int32_t* out_active);
+
+/* IKBase::getSolution() of every run, then what the reference's driver derives from it: exact FK + checkSolution +
+ * computeFitness per run (src/ik_parallel.h:173-181) and the selection among the runs of a query
+ * (src/ik_parallel.h:218-258); outputs as in bioik_solve_islands.  May be called after any bioik_step and does not
+ * disturb the solve. */
+int bioik_get_solution(bioik_ctx* ctx, int32_t wrap, double* out_solutions, double* out_fitness, int32_t* out_success,
+                       int32_t* out_island, int32_t* out_steps);
 
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 int64_t bioik_launch_count(const bioik_ctx* ctx);
