@@ -8,6 +8,7 @@
 #include "bioik_kernels.cuh"
 
 #include <cuda_runtime.h>
+#include <pthread.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -46,6 +47,9 @@ struct RunPlan
     int mg_width = 8, mg_warps = 4;
     size_t mg_smem = 0;
     bool use_mg = false, stale = false;
+    PersistKernel persist = nullptr; // one launch for many steps (bioik_persist.cuh); nullptr: one launch per step and kernel
+    size_t persist_smem = 0;
+    int persist_blocks_per_sm = 0;
 };
 
 struct bioik_ctx
@@ -109,6 +113,12 @@ struct bioik_ctx
     cudaStream_t stream_cancel = nullptr; // so that the copy overtakes a running solve
     int32_t* d_flag = nullptr; // "any run still active" (bioik_solve_islands polls it between bursts)
     int32_t* h_flag = nullptr; // pinned host copy
+    int persist_mode = 0; // BIOIK_PERSIST=1: the persistent solve kernel where it exists (bioik_persist.cuh); 0: stepped launches
+    // work queues of the persistent kernel
+    unsigned long long* d_queue = nullptr;
+    size_t queue_slots = 0;
+    int32_t *d_qctr = nullptr, *d_gcount = nullptr;
+    int gcount_cap = 0;
     bool serial_split = false; // BIOIK_SERIAL_SPLIT=1: one launch per phase of the serial kernel (phase timing study)
     double ms_phase[3] = {0, 0, 0};
 };
@@ -136,6 +146,23 @@ int fail(bioik_ctx* ctx, int code, const std::string& msg)
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// BIOIK_TRACE=1: entry / exit of every ABI call on stderr with the calling thread (debugging of host-side integration)
+struct Trace
+{
+    const char* name;
+    bool on;
+    explicit Trace(const char* n) : name(n)
+    {
+        static const bool enabled = getenv("BIOIK_TRACE") && getenv("BIOIK_TRACE")[0] == '1';
+        on = enabled;
+        if(on) fprintf(stderr, "[bioik %lx] > %s\n", (unsigned long)pthread_self(), name);
+    }
+    ~Trace()
+    {
+        if(on) fprintf(stderr, "[bioik %lx] < %s\n", (unsigned long)pthread_self(), name);
+    }
+};
 
 void drop_graph(bioik_ctx* ctx);
 
@@ -412,6 +439,21 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
         R.use_mg = want_mg && S.memetic && R.mg_smem <= 200 * 1024;
         if(R.stale && !R.use_mg) return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS: problem too large for the lane-group memetic kernel");
         if(R.use_mg && R.mg_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)R.mgk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.mg_smem));
+        // the persistent kernel: same two bodies, fed from device-side queues (one launch for many steps)
+        bool pds = true, pfs = false;
+        R.persist = (ctx->persist_mode && R.fast && R.evolve_lpt == 16 && !R.use_mg && !ctx->serial_split && ctx->serial_plan_force < 0) ? select_persist(P, S.C, &pds, &pfs) : nullptr;
+        if(R.persist)
+        {
+            R.persist_smem = persist_smem_bytes(P, 16, pds, pfs);
+            if(R.persist_smem > 200 * 1024)
+                R.persist = nullptr;
+            else
+            {
+                CU(ctx, cudaFuncSetAttribute((const void*)R.persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.persist_smem));
+                CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&R.persist_blocks_per_sm, (const void*)R.persist, 32 * PERSIST_WARPS, R.persist_smem));
+                if(R.persist_blocks_per_sm < 1) R.persist = nullptr;
+            }
+        }
     }
     else if(ctx->stale_tips && S.memetic && stale_tips_matter(P))
         return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS is not available with BIOIK_FORCE_GENERIC");
@@ -473,7 +515,51 @@ int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
     const DProblem& P = ctx->hP;
     const int B = S.B, TPB = 128, warps_per_block = BIOIK_EVOLVE_WPB;
     const int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    if(!ctx->force_generic)
+    if(!ctx->force_generic && R.persist)
+    {
+        // One launch per burst of steps.  With the driver's `finished` flag among islands that span several serial groups
+        // (early_exit 2) the bursts end at the 4-step tests: a success recorded by one group must not be seen by a group that is
+        // a step behind or ahead inside the same launch (the stepped path is in lock step by construction).
+        const bool lockstep = S.early_exit == 2 && S.islands > PERSIST_GROUP_QUERIES;
+        const int groups = (B + PERSIST_GROUP_QUERIES - 1) / PERSIST_GROUP_QUERIES;
+        int a = s0;
+        while(a < s1)
+        {
+            int b = std::min(s1, a + 64);
+            if(lockstep) b = std::min(b, (a / 4 + 1) * 4);
+            const bool last_here = last && b == s1;
+            PersistArgs A;
+            A.s0 = a, A.s1 = b, A.last = last_here ? 1 : 0, A.prepared = R.prepared ? 1 : 0, A.groups = groups, A.sm_count = ctx->sm_count;
+            A.cap_e = (b - a) * B, A.cap_s = (b - a + 1) * groups;
+            const size_t need = (size_t)A.cap_e + (size_t)A.cap_s;
+            if(need > ctx->queue_slots || groups > ctx->gcount_cap || !ctx->d_qctr)
+            {
+                drop_graph(ctx);
+                CU(ctx, cudaDeviceSynchronize());
+                cudaFree(ctx->d_queue), cudaFree(ctx->d_gcount), cudaFree(ctx->d_qctr);
+                ctx->d_queue = nullptr, ctx->d_gcount = nullptr, ctx->d_qctr = nullptr, ctx->queue_slots = 0, ctx->gcount_cap = 0;
+                CU(ctx, cudaMalloc(&ctx->d_queue, need * 8));
+                CU(ctx, cudaMalloc(&ctx->d_gcount, (size_t)groups * 4));
+                CU(ctx, cudaMalloc(&ctx->d_qctr, PQ_INTS * 4));
+                CU(ctx, cudaMemset(ctx->d_qctr, 0, PQ_INTS * 4));
+                ctx->queue_slots = need, ctx->gcount_cap = groups;
+            }
+            A.slots_e = ctx->d_queue, A.slots_s = ctx->d_queue + A.cap_e, A.ctr = ctx->d_qctr, A.gcount = ctx->d_gcount;
+            const int fill = std::max(std::max(A.cap_e, A.cap_s), groups);
+            Timed tm(ctx, st, 0);
+            k_persist_init<<<(fill + 255) / 256, 256, 0, st>>>(A, B);
+            if((rc = check_launch(ctx, "k_persist_init")) != BIOIK_OK) return rc;
+            int blocks = std::max(groups, (B + PERSIST_WARPS - 1) / PERSIST_WARPS);
+            blocks = std::max(1, std::min(blocks, ctx->sm_count * R.persist_blocks_per_sm));
+            R.persist<<<blocks, 32 * PERSIST_WARPS, R.persist_smem, st>>>(ctx->hP, ctx->dP, S, A, ctx->d_mtab);
+            rc = check_launch(ctx, "k_persist");
+            tm.done();
+            if(rc != BIOIK_OK) return rc;
+            R.prepared = !last_here;
+            a = b;
+        }
+    }
+    else if(!ctx->force_generic)
     {
         if(!R.prepared)
         {
@@ -546,6 +632,16 @@ int count_active(bioik_ctx* ctx, cudaStream_t st, int step, int* out)
     return BIOIK_OK;
 }
 
+// after a stream synchronisation of a solve that used the persistent kernel: did its watchdog fire?
+int check_watchdog(bioik_ctx* ctx)
+{
+    if(!ctx->run.persist || !ctx->d_qctr) return BIOIK_OK;
+    int32_t fired = 0;
+    CU(ctx, cudaMemcpy(&fired, ctx->d_qctr + PQ_ABORT, 4, cudaMemcpyDeviceToHost));
+    if(fired) return fail(ctx, BIOIK_E_CUDA, "persistent solve kernel: watchdog fired (no work item became available for seconds); results are invalid");
+    return BIOIK_OK;
+}
+
 // getSolution() of every run: full variable vector, primary fitness, success test, step count
 int solve_finish(bioik_ctx* ctx, cudaStream_t st, double* d_osol, double* d_ofit, int32_t* d_osucc, int32_t* d_osteps)
 {
@@ -594,6 +690,7 @@ const char* bioik_last_error(const bioik_ctx* ctx) { return ctx ? ctx->error.c_s
 
 int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx** out)
 {
+    Trace trace_("bioik_create");
     if(!robot || !cfg || !out) return fail(nullptr, BIOIK_E_INVALID, "null argument");
     *out = nullptr;
     if(cfg->population < 4 || cfg->population > 32 * EVOLVE_MAX_CPL) return fail(nullptr, BIOIK_E_LIMIT, "population must be in [4, 256]");
@@ -649,6 +746,8 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
         if(ch && atoi(ch) > 0) ctx->ch_cap = atoi(ch);
         const char* mg = getenv("BIOIK_MEMETIC_GROUP");
         ctx->memetic_group = mg ? (mg[0] == '0' ? 0 : 1) : -1;
+        const char* pm = getenv("BIOIK_PERSIST");
+        if(pm) ctx->persist_mode = atoi(pm);
         const char* sp = getenv("BIOIK_SERIAL_SPLIT");
         ctx->serial_split = sp && sp[0] == '1';
     }
@@ -658,6 +757,7 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
 
 void bioik_destroy(bioik_ctx* ctx)
 {
+    Trace trace_("bioik_destroy");
     if(!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
@@ -667,6 +767,7 @@ void bioik_destroy(bioik_ctx* ctx)
     cudaFree(ctx->d_uniform), cudaFree(ctx->d_gauss), cudaFree(ctx->dP), cudaFree(ctx->d_gauss_off), cudaFree(ctx->d_rate_exp), cudaFree(ctx->d_mtab), cudaFree(ctx->state_block);
     cudaFree(ctx->d_gp), cudaFree(ctx->d_seeds), cudaFree(ctx->d_rs), cudaFree(ctx->d_osol), cudaFree(ctx->d_ofit), cudaFree(ctx->d_osucc), cudaFree(ctx->d_osteps), cudaFree(ctx->d_default_gp);
     cudaFree(ctx->d_flag), cudaFree(ctx->d_cancel);
+    cudaFree(ctx->d_queue), cudaFree(ctx->d_qctr), cudaFree(ctx->d_gcount);
     if(ctx->h_one) cudaFreeHost(ctx->h_one);
     if(ctx->stream_cancel) cudaStreamDestroy(ctx->stream_cancel);
     if(ctx->h_flag) cudaFreeHost(ctx->h_flag);
@@ -677,6 +778,7 @@ void bioik_destroy(bioik_ctx* ctx)
 
 int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
 {
+    Trace trace_("bioik_set_problem");
     if(!ctx || !problem) return fail(ctx, BIOIK_E_INVALID, "null argument");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -712,6 +814,7 @@ int bioik_set_problem(bioik_ctx* ctx, const BioikProblem* problem)
 int bioik_solve_batch_device(bioik_ctx* ctx, int32_t B, const double* d_goal_params, const double* d_seeds, const uint32_t* d_rng_seeds, int32_t steps, int32_t early_exit, double* d_out_solutions, double* d_out_fitness,
                              int32_t* d_out_success, int32_t* d_out_steps, void* cuda_stream)
 {
+    Trace trace_("bioik_solve_batch_device");
     if(!ctx) return BIOIK_E_INVALID;
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
@@ -722,6 +825,7 @@ int bioik_solve_batch_device(bioik_ctx* ctx, int32_t B, const double* d_goal_par
 int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, double* out_solutions, double* out_fitness, int32_t* out_success,
                       int32_t* out_steps)
 {
+    Trace trace_("bioik_solve_batch");
     if(!ctx) return BIOIK_E_INVALID;
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
     if(B <= 0 || !seeds || !rng_seeds) return fail(ctx, BIOIK_E_INVALID, "bad solve arguments");
@@ -780,7 +884,7 @@ int bioik_solve_batch(bioik_ctx* ctx, int32_t B, const double* goal_params, cons
     if(out_success) CU(ctx, cudaMemcpyAsync(out_success, ctx->d_osucc, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if(out_steps) CU(ctx, cudaMemcpyAsync(out_steps, ctx->d_osteps, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
-    return BIOIK_OK;
+    return check_watchdog(ctx);
 }
 
 int bioik_cancel(bioik_ctx* ctx)
@@ -807,6 +911,7 @@ int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value)
 
 int bioik_begin(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t max_steps, int32_t early_exit)
 {
+    Trace trace_("bioik_begin");
     if(!ctx) return BIOIK_E_INVALID;
     if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
     if(Q <= 0 || islands <= 0 || max_steps < 0 || !seeds || !rng_seeds || (int64_t)Q * islands > (int64_t)INT32_MAX / 4) return fail(ctx, BIOIK_E_INVALID, "bad bioik_begin arguments");
@@ -853,6 +958,7 @@ int bioik_begin(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_p
 
 int bioik_step(bioik_ctx* ctx, int32_t nsteps, int32_t* out_active)
 {
+    Trace trace_("bioik_step");
     if(!ctx) return BIOIK_E_INVALID;
     if(!ctx->run.open || ctx->run.islands <= 0) return fail(ctx, BIOIK_E_INVALID, "bioik_step without bioik_begin");
     if(nsteps < 0) return fail(ctx, BIOIK_E_INVALID, "negative step count");
@@ -868,11 +974,12 @@ int bioik_step(bioik_ctx* ctx, int32_t nsteps, int32_t* out_active)
         *out_active = active;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return BIOIK_OK;
+    return check_watchdog(ctx);
 }
 
 int bioik_get_solution(bioik_ctx* ctx, int32_t wrap, double* out_solutions, double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
 {
+    Trace trace_("bioik_get_solution");
     if(!ctx) return BIOIK_E_INVALID;
     if(!ctx->run.open || ctx->run.islands <= 0) return fail(ctx, BIOIK_E_INVALID, "bioik_get_solution without bioik_begin");
     if(!out_solutions) return fail(ctx, BIOIK_E_INVALID, "out_solutions is required");
@@ -898,6 +1005,7 @@ int bioik_get_solution(bioik_ctx* ctx, int32_t wrap, double* out_solutions, doub
 int bioik_solve_islands(bioik_ctx* ctx, int32_t Q, int32_t islands, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int32_t steps, int32_t early_exit, int32_t wrap, double* out_solutions,
                         double* out_fitness, int32_t* out_success, int32_t* out_island, int32_t* out_steps)
 {
+    Trace trace_("bioik_solve_islands");
     if(!ctx) return BIOIK_E_INVALID;
     if(!out_solutions || steps < 0) return fail(ctx, BIOIK_E_INVALID, "bad solve_islands arguments");
     int rc = bioik_begin(ctx, Q, islands, goal_params, seeds, rng_seeds, steps, early_exit);
@@ -1030,6 +1138,18 @@ int bioik_kernel_time(bioik_ctx* ctx, int32_t reset, double* out_ms_evolve, int6
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     CU(ctx, cudaDeviceSynchronize());
     drain_events(ctx);
+#ifdef BIOIK_PERSIST_STATS
+    if(ctx->d_qctr)
+    {
+        unsigned long long st[8];
+        cudaMemcpy(st, ctx->d_qctr + PQ_STATS, sizeof(st), cudaMemcpyDeviceToHost);
+        if(st[7])
+            fprintf(stderr, "[bioik] persistent kernel, per warp-launch averages over %llu warp-launches: resident %.0f cycles = evolve %.0f (%.2f items of %.0f) + serial %.0f (%.2f items of %.0f) + idle %.0f (%.1f polls)\n", st[7],
+                    (double)st[6] / st[7], (double)st[0] / st[7], (double)st[3] / st[7], st[3] ? (double)st[0] / st[3] : 0.0, (double)st[1] / st[7], (double)st[4] / st[7], st[4] ? (double)st[1] / st[4] : 0.0,
+                    (double)st[2] / st[7], (double)st[5] / st[7]);
+        if(reset) cudaMemset(ctx->d_qctr + PQ_STATS, 0, sizeof(st));
+    }
+#endif
     if(ctx->serial_split && ctx->n_serial)
         fprintf(stderr, "[bioik] serial phases (ms total): memetic %.3f species %.3f prepare %.3f over %lld launches\n", ctx->ms_phase[0], ctx->ms_phase[1], ctx->ms_phase[2], (long long)ctx->n_serial);
     if(reset) ctx->ms_phase[0] = ctx->ms_phase[1] = ctx->ms_phase[2] = 0;

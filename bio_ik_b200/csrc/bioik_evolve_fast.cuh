@@ -338,25 +338,20 @@ template <bool JOINT> __device__ __forceinline__ double fast_eval_one_tips(const
 // LPT (lanes per task): 32 = one warp per task; 16 / 8 = two / four tasks per warp, each lane then owns 8 / 16 children.  The
 // per-child work is lane-efficient either way, but the per-generation overhead (tables, the two argmin reductions, winner
 // re-derivation: ~37 % of the instructions at LPT 32) is issued once per WARP, i.e. shared by the tasks of the warp.
-template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int LPT = 32> __global__ void __launch_bounds__(32 * BIOIK_EVOLVE_WPB, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// The body of the generation kernel for ONE task = (query, species slot): `generations` x {reproduce, phenotype, fitness, selection}
+// of step `step`, run by the LPT lanes `gmask` of a warp (lane = index inside that group, lane0 = its first warp lane) on the
+// shared-memory block W (FastSmem::total() doubles).  Called by k_evolve_fast (one launch per step) and by the persistent
+// solve kernel (bioik_persist.cuh), which keeps warps resident and feeds them (query, step) items from a queue.
+template <int T, int CH, int GSPEC, bool JOINT, int NG, bool TM, int LPT>
+__device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState& S, int step, const double* __restrict__ mtab, double* W, int task, int lane, int lane0, unsigned gmask)
 {
-    extern __shared__ double smem[];
-    const DProblem& P = *Pp;
     static_assert(LPT == 32 || (LPT == 16 || LPT == 8) && !TM && GSPEC == 1 && !JOINT, "lane groups are instantiated for the single-pose problem only");
-    constexpr int TPW = 32 / LPT;            // tasks per warp
-    const int lane = (threadIdx.x & 31) % LPT; // lane within the task's group
-    const int grp = (threadIdx.x & 31) / LPT;
-    const int lane0 = grp * LPT;             // first warp lane of the group
-    const unsigned gmask = LPT == 32 ? 0xffffffffu : (((1u << LPT) - 1u) << lane0); // the group's lanes: every warp-level primitive below is group-wide
-    const int warp_in_block = threadIdx.x >> 5;
-    const int task = (blockIdx.x * (blockDim.x >> 5) + warp_in_block) * TPW + grp;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
     if(run_done(S, q, step)) return;
     const int n = NG ? NG : P.n, C = S.C, G = P.G;
     const int R = mtab_row(C);
     const int nchunks = R / (LPT * CH); // R is a power of two >= LPT * CH (select_evolve_fast)
-
     // joint-space goals in goal order: slot j of the accumulators = the j-th of them; avoid_j = AvoidJointLimitsGoal
     int nj = 0;
     bool jq_avoid[FAST_MAX_JOINT_GOALS];
@@ -374,7 +369,6 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
 
     FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1};
     const int TT = TM ? P.T : T; // tips of the problem
-    double* W = smem + (size_t)(warp_in_block * TPW + grp) * L.total();
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
     double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf(), *s_gv = W + L.off_gv();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
@@ -888,6 +882,22 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
     }
 }
 
+template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int LPT = 32> __global__ void __launch_bounds__(32 * BIOIK_EVOLVE_WPB, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+{
+    extern __shared__ double smem[];
+    const DProblem& P = *Pp;
+    constexpr int TPW = 32 / LPT;              // tasks per warp
+    const int lane = (threadIdx.x & 31) % LPT; // lane within the task's group
+    const int grp = (threadIdx.x & 31) / LPT;
+    const int lane0 = grp * LPT;               // first warp lane of the group
+    const unsigned gmask = LPT == 32 ? 0xffffffffu : (((1u << LPT) - 1u) << lane0); // the group's lanes: every warp-level primitive of the body is group-wide
+    const int warp_in_block = threadIdx.x >> 5;
+    const int task = (blockIdx.x * (blockDim.x >> 5) + warp_in_block) * TPW + grp;
+    const int n = NG ? NG : P.n;
+    FastSmem L{n, TM ? P.T : T, P.G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1};
+    evolve_fast_task<T, CH, GSPEC, JOINT, NG, TM, LPT>(P, S, step, mtab, smem + (size_t)(warp_in_block * TPW + grp) * L.total(), task, lane, lane0, gmask);
+}
+
 typedef void (*EvolveFastKernel)(const DProblem*, DState, int, const double*);
 
 // picks the instantiation for (tips, population, goals); returns nullptr if the generic kernel must be used
@@ -904,13 +914,20 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
     if(J && cpl > 2) cpl = 2;      // joint-space accumulators on top of the frame accumulators: blocks of 4 spill (cfg4: 29.5 vs 21.8 ms per pass)
 #define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
-    if(single_pose && cpl >= 3 && (P.n == 7 || P.n == 6) && ch_cap >= 8)
+    if(single_pose && (P.n == 7 || P.n == 6) && ch_cap >= 8)
     {
-        // lane groups: R / (LPT * 4) chunks of 4 children per lane; R >= 128 here
-        const int lpt = lanes_per_task ? (lpt_want <= 8 ? 8 : (lpt_want <= 16 ? 16 : 32)) : 32;
+        // lane groups: LPT lanes per task, R / (LPT * CH) chunks of CH children per lane.  R >= 128: 8, 16 or 32 lanes as wanted,
+        // blocks of 4; R = 64 (population <= 66): 16 or 8 lanes; R = 32 (population <= 34, the reference's 18): 16 lanes, blocks of 2
+        const int R = mtab_row(C);
+        int lpt = lanes_per_task ? (lpt_want <= 8 ? 8 : (lpt_want <= 16 ? 16 : 32)) : 32;
+        if(R == 64 && lpt == 32) lpt = 16;
+        if(R == 32) lpt = lanes_per_task ? 16 : 32;
         if(lanes_per_task) *lanes_per_task = lpt;
-        if(P.n == 7) return lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 7>);
-        return lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, 6>);
+#define BIOIK_PICK_LG(NN)                                                                                                                                              \
+    (R == 32 ? (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false, NN, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>)                          \
+             : (lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN>)))
+        return P.n == 7 ? BIOIK_PICK_LG(7) : BIOIK_PICK_LG(6);
+#undef BIOIK_PICK_LG
     }
     if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
     if(T == 1) return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));

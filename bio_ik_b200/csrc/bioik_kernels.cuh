@@ -684,3 +684,4 @@ __global__ void k_approx_fitness(const DProblem* __restrict__ Pp, int B, int M, 
 #include "bioik_evolve_fast.cuh"
 #include "bioik_serial.cuh"
 #include "bioik_memetic_group.cuh"
+#include "bioik_persist.cuh"

@@ -210,17 +210,16 @@ BIOIK_HD void memetic_single_pose(const DProblem& P, const DState& S, IndCol ind
 }
 
 // BS = threads per block (column stride), DS = delta frames in shared memory, FS = link frames in shared memory
-template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_serial(BIOIK_PROBLEM_PARAM, DState S, int step, int phases)
+// The serial work of BS tasks, one thread each (tid = the thread's column in `smem`, task_raw = its task).  Called by k_serial
+// (one block of BS threads per call) and by the persistent solve kernel (bioik_persist.cuh: one warp, BS = 32).
+template <int BS, bool DS, bool FS> __device__ __forceinline__ void serial_tasks(const DProblem& P, const DState& S, int step, int phases, double* smem, int tid, int task_raw)
 {
-    extern __shared__ double smem[];
     typedef FixedCol<double, BS> SC;         // shared-memory column
     typedef FixedCol<const double, BS> CSC;
     typedef FixedCol<double, 1> GC;          // plain array (global / local)
     typedef typename std::conditional<DS, SC, GC>::type DeltaCol;
     typedef typename std::conditional<FS, SC, GC>::type FrameCol;
 
-    const int tid = threadIdx.x;
-    const int task_raw = blockIdx.x * BS + tid;
     const bool valid = task_raw < 2 * S.B;
     const int task = valid ? task_raw : 2 * S.B - 1;
     const int q = task >> 1, slot = task & 1;
@@ -603,6 +602,12 @@ template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_seri
                 store_frame(d0 + ((size_t)t * n + i) * 7, df);
             }
     }
+}
+
+template <int BS, bool DS, bool FS> __global__ void __launch_bounds__(BS) k_serial(BIOIK_PROBLEM_PARAM, DState S, int step, int phases)
+{
+    extern __shared__ double smem[];
+    serial_tasks<BS, DS, FS>(P, S, step, phases, smem, threadIdx.x, blockIdx.x * BS + threadIdx.x);
 }
 
 #ifdef BIOIK_HOSTSIM

@@ -135,6 +135,11 @@ int adapter_parallel(const BioikRobot* robot, const BioikProblem* problem, const
         if(out_success) *out_success = ik.getSuccess() ? 1 : 0;
         if(out_fitness) *out_fitness = ik.getSolutionFitness();
         if(out_iterations) *out_iterations = (int32_t)ik.iteration_count;
+        // ~ParallelExecutor (src/ik_parallel.h:80-86) sets `exit` and then meets its workers at the barrier, assuming they are back at
+        // the top of their loop.  A worker that has not yet passed the `if(exit) break;` after the END barrier of run() (:67-68)
+        // would leave instead and the destructor would wait forever - a teardown race of the reference that a long-lived plugin
+        // never meets, but a harness destroying the driver microseconds after solve() does.  Give the workers time to loop around.
+        if(thread_count > 1) std::this_thread::sleep_for(std::chrono::milliseconds(50));
         return 0;
     }
     catch(std::exception& e)

@@ -81,6 +81,28 @@ static inline int atomicMin(int* a, int v)
     if(v < old) *a = v;
     return old;
 }
+// the queue operations of the persistent kernel: in the simulation only one lane of the single resident warp executes them at a time
+static inline int atomicAdd(int* a, int v)
+{
+    int old = *a;
+    *a = old + v;
+    return old;
+}
+static inline int atomicCAS(int* a, int cmp, int v)
+{
+    int old = *a;
+    if(old == cmp) *a = v;
+    return old;
+}
+static inline int atomicExch(int* a, int v)
+{
+    int old = *a;
+    *a = v;
+    return old;
+}
+static inline void __threadfence() {}
+using std::max;
+using std::min;
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline double __longlong_as_double(long long v)
 {
@@ -255,8 +277,40 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
         pl.block = 32;
         SerialKernel ks = select_serial(pl);
         const int sgrid = (2 * B + 31) / 32;
-        if(steps > 0) launch_warp(sgrid, [&]() { ks(P, S, 0, PH_PREPARE); });
-        for(int step = 0; step < steps; step++)
+        bool pds = true, pfs = false;
+        PersistKernel pk = use_fast == 10 ? select_persist(P, S.C, &pds, &pfs) : nullptr;
+        if(use_fast == 10 && (!pk || !fast || evolve_lpt != 16))
+        {
+            g_err = "no persistent kernel for this problem shape";
+            return 1;
+        }
+        if(pk)
+        {
+            // the persistent kernel (bioik_persist.cuh) with ONE resident warp: it drains both queues by itself, which exercises
+            // the whole dependency logic (PREPARE items, group counters, the hand-over between evolve and serial items); two
+            // launches with a cut in the middle exercise the resume path of bioik_step
+            const int groups = (B + PERSIST_GROUP_QUERIES - 1) / PERSIST_GROUP_QUERIES;
+            std::vector<unsigned long long> slots((size_t)(steps + 1) * (B + groups) + 8);
+            std::vector<int32_t> ctr(PQ_INTS), gcount(groups);
+            bool prepared = false;
+            const int cut = steps / 2;
+            for(int part = 0; part < 2; part++)
+            {
+                const int a = part ? cut : 0, b = part ? steps : cut;
+                if(b <= a) continue;
+                PersistArgs A;
+                A.s0 = a, A.s1 = b, A.last = b == steps ? 1 : 0, A.prepared = prepared ? 1 : 0, A.groups = groups, A.sm_count = 1;
+                A.cap_e = (b - a) * B, A.cap_s = (b - a + 1) * groups;
+                A.slots_e = slots.data(), A.slots_s = slots.data() + A.cap_e, A.ctr = ctr.data(), A.gcount = gcount.data();
+                const int fill = std::max(std::max(A.cap_e, A.cap_s), groups);
+                launch_serial((fill + 255) / 256, 256, [&]() { k_persist_init(A, B); });
+                launch_warp(1, [&]() { pk(P, &P, S, A, mtab.data()); });
+                prepared = b != steps;
+            }
+        }
+        else if(steps > 0)
+            launch_warp(sgrid, [&]() { ks(P, S, 0, PH_PREPARE); });
+        for(int step = 0; step < steps && !pk; step++)
         {
             if(fast)
                 launch_warp((2 * B + 32 / evolve_lpt - 1) / (32 / evolve_lpt), [&]() { fast(&P, S, step, mtab.data()); });

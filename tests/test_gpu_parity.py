@@ -234,7 +234,7 @@ def test_device_pointer_entry_point(oracle):
     ref = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)
     assert np.array_equal(sol.cpu().numpy(), ref["solutions"]) and np.array_equal(fit.cpu().numpy(), ref["fitness"])
     ev, nev, se, nse = solver.kernel_time(disable=True)
-    assert nev >= 6 and ev > 0 and solver.launch_count() > 0
+    assert nev >= 1 and ev > 0 and solver.launch_count() > 0  # one launch per step in the stepped path, one per solve in the persistent one
     # with timing off, repeated host-API solves of one shape replay a CUDA graph: same answers
     for _ in range(3):
         again = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)

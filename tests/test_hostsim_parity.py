@@ -210,3 +210,16 @@ def test_mimic_joints(sim, oracle):
         b = sim.solve(rm, pr, cfg, gp, seeds, rs, 5, fast=fast)
         for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
             assert np.array_equal(a[k], b[k]), (k, fast)
+
+
+@pytest.mark.parametrize("B,pop,mode,steps,early", [(5, 128, "q", 5, False), (19, 64, "q", 3, False), (33, 128, "l", 2, False), (18, 128, "q", 9, True), (3, 200, 0, 3, False)])
+def test_persistent_kernel_is_bit_identical_to_the_oracle(sim, oracle, B, pop, mode, steps, early):
+    """bioik_persist.cuh: the whole solve as work items (evolve(query, step), serial(group of 16 queries, step)) taken from two
+    queues by resident warps - here by ONE simulated warp, in two launches with a cut in the middle (the resume path of
+    bioik_step).  Partial groups (B not a multiple of 16), several groups, early exit and the non-memetic mode included."""
+    w = workloads.make("cfg2", lambda rm, pr, v: oracle.fk(rm, pr, v), batch=B)
+    cfg = oracle_lib.make_cfg(population=pop, memetic=mode, generations=8 if mode else 16)
+    a = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, early_exit=early)
+    b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, early_exit=early, fast=10)
+    for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps") if not early else ("solutions", "fitness", "success", "steps"):
+        assert np.array_equal(a[k], b[k]), k
