@@ -91,7 +91,7 @@ LIB_PATH = os.environ.get("BIOIK_LIB") or os.path.join(REPO_ROOT, "bio_ik_b200",
 ABI_SYMBOLS = [
     "bioik_create", "bioik_destroy", "bioik_set_problem", "bioik_solve_batch", "bioik_solve_batch_device",
     "bioik_synchronize", "bioik_fk_batch", "bioik_approx_batch", "bioik_approx_fitness_batch",
-    "bioik_solve_batch_trace", "bioik_solve_islands", "bioik_begin", "bioik_step", "bioik_get_solution", "bioik_set_option", "bioik_cancel", "bioik_launch_count", "bioik_kernel_time", "bioik_last_error", "bioik_abi_version",
+    "bioik_solve_batch_trace", "bioik_solve_islands", "bioik_begin", "bioik_step", "bioik_get_solution", "bioik_pack_results_device", "bioik_kernel_name", "bioik_set_option", "bioik_cancel", "bioik_launch_count", "bioik_kernel_time", "bioik_last_error", "bioik_abi_version",
 ]
 
 _lib = None
@@ -143,6 +143,10 @@ def load_library(path=None):
     lib.bioik_step.restype = C.c_int
     lib.bioik_get_solution.argtypes = [ctx_p, C.c_int32, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]
     lib.bioik_get_solution.restype = C.c_int
+    lib.bioik_pack_results_device.argtypes = [ctx_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bioik_pack_results_device.restype = C.c_int
+    lib.bioik_kernel_name.argtypes = [ctx_p]
+    lib.bioik_kernel_name.restype = C.c_char_p
     lib.bioik_cancel.argtypes = [ctx_p]
     lib.bioik_cancel.restype = C.c_int
     lib.bioik_set_option.argtypes = [ctx_p, C.c_int32, C.c_int32]

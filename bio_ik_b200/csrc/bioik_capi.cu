@@ -47,6 +47,7 @@ struct RunPlan
     int mg_width = 8, mg_warps = 4;
     size_t mg_smem = 0;
     bool use_mg = false, stale = false;
+    const char* dominant = ""; // instantiation name of the kernel bioik_kernel_time times as "generation" work
     PersistKernel persist = nullptr; // one launch for many steps (bioik_persist.cuh); nullptr: one launch per step and kernel
     size_t persist_smem = 0;
     int persist_blocks_per_sm = 0;
@@ -69,6 +70,7 @@ struct bioik_ctx
     DProblem* dP = nullptr;
 
     double *d_uniform = nullptr, *d_gauss = nullptr;
+    double gauss_absmax = 0; // max |gauss| of the lookup table
 
     // schedules (depend on steps, gens, C, n)
     int sched_steps = -1, sched_n = -1;
@@ -342,6 +344,16 @@ int check_launch(bioik_ctx* ctx, const char* what)
     return BIOIK_OK;
 }
 
+// [B][n_vars + 3] result slab of the multi-GPU gather: solution | fitness | success | steps (bio_ik_b200/distributed.py)
+__global__ void k_pack_results(int B, int n_vars, const double* __restrict__ sol, const double* __restrict__ fit, const int32_t* __restrict__ succ, const int32_t* __restrict__ steps, double* __restrict__ slab)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = n_vars + 3;
+    if(i >= (size_t)B * W) return;
+    const int q = (int)(i / W), c = (int)(i - (size_t)q * W);
+    slab[i] = c < n_vars ? sol[(size_t)q * n_vars + c] : (c == n_vars ? fit[q] : (c == n_vars + 1 ? (double)succ[q] : (double)steps[q]));
+}
+
 __global__ void k_broadcast(const double* __restrict__ src, int per, int B, double* __restrict__ dst)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,6 +398,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     S.rng_seeds = d_rs;
     S.uniform = ctx->d_uniform;
     S.gauss = ctx->d_gauss;
+    S.gauss_absmax = ctx->gauss_absmax;
 
     // launch plan of the step kernels
     RunPlan& R = ctx->run;
@@ -394,6 +407,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     R.next_step = 0;
     R.evolve_lpt = 32;
     R.fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &R.evolve_lpt, ctx->lpt_want);
+    R.dominant = R.fast ? selected_kernel_name() : "k_evolve";
     const int warps_per_block = BIOIK_EVOLVE_WPB;
     if(R.fast)
     {
@@ -454,6 +468,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
                 if(R.persist_blocks_per_sm < 1) R.persist = nullptr;
             }
         }
+        if(R.persist) R.dominant = selected_kernel_name();
     }
     else if(ctx->stale_tips && S.memetic && stale_tips_matter(P))
         return fail(ctx, BIOIK_E_LIMIT, "BIOIK_OPT_REFERENCE_STALE_TIPS is not available with BIOIK_FORCE_GENERIC");
@@ -722,6 +737,7 @@ int bioik_create(const BioikRobot* robot, const BioikSolverCfg* cfg, bioik_ctx**
     {
         std::vector<double> u, g;
         make_tables(cfg->table_seed, u, g);
+        for(double v : g) ctx->gauss_absmax = std::max(ctx->gauss_absmax, std::fabs(v));
         e = cudaMemcpy(ctx->d_uniform, u.data(), u.size() * 8, cudaMemcpyHostToDevice);
         if(e == cudaSuccess) e = cudaMemcpy(ctx->d_gauss, g.data(), g.size() * 8, cudaMemcpyHostToDevice);
     }
@@ -1129,6 +1145,20 @@ int bioik_approx_fitness_batch(bioik_ctx* ctx, int32_t B, int32_t M, const doubl
     cudaFree(d_gp), cudaFree(d_seed), cudaFree(d_base), cudaFree(d_gen), cudaFree(d_p), cudaFree(d_s), cudaFree(d_scr);
     return rc;
 }
+
+int bioik_pack_results_device(bioik_ctx* ctx, int32_t B, const double* d_solutions, const double* d_fitness, const int32_t* d_success, const int32_t* d_steps, double* d_slab, void* cuda_stream)
+{
+    if(!ctx) return BIOIK_E_INVALID;
+    if(!ctx->has_problem) return fail(ctx, BIOIK_E_NO_PROBLEM, "bioik_set_problem has not been called");
+    if(B <= 0 || !d_solutions || !d_fitness || !d_success || !d_steps || !d_slab) return fail(ctx, BIOIK_E_INVALID, "bad pack arguments");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    const size_t total = (size_t)B * (ctx->hP.n_vars + 3);
+    k_pack_results<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ctx->hP.n_vars, d_solutions, d_fitness, d_success, d_steps, d_slab);
+    return check_launch(ctx, "k_pack_results");
+}
+
+const char* bioik_kernel_name(const bioik_ctx* ctx) { return ctx ? ctx->run.dominant : ""; }
 
 int64_t bioik_launch_count(const bioik_ctx* ctx) { return ctx ? ctx->launches : 0; }
 

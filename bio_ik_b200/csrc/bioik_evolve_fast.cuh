@@ -346,6 +346,9 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG, bool TM, int LPT>
 __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState& S, int step, const double* __restrict__ mtab, double* W, int task, int lane, int lane0, unsigned gmask)
 {
     static_assert(LPT == 32 || (LPT == 16 || LPT == 8) && !TM && GSPEC == 1 && !JOINT, "lane groups are instantiated for the single-pose problem only");
+    // the single-pose problem with a compile-time gene count (NG <= 8 genes sit in the first lanes of a lane group; with 16 lanes per
+    // task both groups of a warp hold the two species of one query, so they enter and leave together and warp-wide votes are safe)
+    constexpr bool LEAN = NG != 0 && NG <= 8 && GSPEC == 1 && !JOINT && !TM && (LPT == 16 || LPT == 32);
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
     if(run_done(S, q, step)) return;
@@ -451,6 +454,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         const double *p_g0 = par, *p_g1 = par + n, *p_gr0 = par + 2 * n, *p_gr1 = par + 3 * n;
 
         // per-generation warp-uniform tables: pg = mix(gr0, gr1, fmix), term = pg * gradient_factor  (:268-269,:294-295)
+        bool gene_safe = false;
         for(int i = lane; i < n; i += LPT)
         {
             double a = p_gr0[i], b = p_gr1[i];
@@ -465,6 +469,24 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             s_term[6 * i + 4] = pgo * 1.0;
             s_term[6 * i + 5] = pgo * 2.0;
             s_rec[4 * i + 0] = p_g0[i];
+            if(LEAN)
+            {
+                // Clamp elision: every child gene of this generation is fl(fl(g0 + m) + t) with |m| <= gauss_absmax * 2^-8 * span
+                // (mutation_rate <= 2^15 / 2^23, :265,:290-293) and t in {0, pg, 2 pg} (:294-296).  If g0 keeps that distance (plus
+                // rounding slack) from both clip limits, clamp() returns its argument for all children and is skipped for the gene.
+                const double g0 = p_g0[i];
+                const double e = (S.gauss_absmax * (1.0 / 256.0) * P.genes[i].span + 2.0 * BIOIK_FMAX(BIOIK_FABS(pge), BIOIK_FABS(pgo))) * 1.000001;
+                const double slack = e + 1e-15 * (BIOIK_FABS(g0) + e);
+#ifndef BIOIK_X_NOELIDE
+                gene_safe = (g0 - slack > s_rec[4 * i + 2]) && (g0 + slack < s_rec[4 * i + 3]); // false for NaN: the clamp stays
+#endif
+            }
+        }
+        unsigned unclamped = 0u; // bit i: gene i needs no clamp in this generation, for every task of the warp (warp-uniform)
+        if(LEAN)
+        {
+            const unsigned safe = __ballot_sync(0xffffffffu, gene_safe);
+            unclamped = LPT == 16 ? (safe & (safe >> 16)) : safe; // lanes 0..NG-1 of every lane group hold the genes
         }
         __syncwarp(gmask);
 
@@ -585,8 +607,17 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                         double gene = g0;
                         gene += m[k];                // gene += r * f      (:293)
                         gene += tp[k][0];            // gene += gradient   (:296)
-                        gene = clampd(gene, lo, hi); // :297
                         x[k] = gene;
+                    }
+                    if(!(LEAN && ((unclamped >> i) & 1u))) // :297 (warp-uniform: skipped where clamp() is the identity for every child)
+                    {
+#pragma unroll
+                        for(int k = 0; k < CH; k++) x[k] = clampd(x[k], lo, hi);
+                    }
+#pragma unroll
+                    for(int k = 0; k < CH; k++)
+                    {
+                        const double gene = x[k];
                         d[k] = gene - base; // :1086
                         tp[k] += 6;
                     }
@@ -652,7 +683,6 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                     }
                     if(i < n) gene_step(std::false_type{}, i, mB, mA);
                 }
-
             }
 
             // fitness: weighted sum in goal order (src/problem.cpp:251-257)
@@ -661,6 +691,26 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             {
                 const int c = jbase + LPT * k + 2;
                 double prim = 0.0, sec = 0.0;
+                if(LEAN)
+                {
+                    // PoseGoal::evaluate * weight_sq (goal_types.h:149-180, problem.cpp:251-257) without the additions to a zero
+                    // accumulator (exact: every summand is >= +0 or NaN) and with fmin as a select (both norms are NaN together)
+                    const double* f = F[k][0];
+                    const double e_pos = len2(s_gp[0] - f[0], s_gp[1] - f[1], s_gp[2] - f[2]);
+                    const double qm = qlen2(s_gp[3] - f[3], s_gp[4] - f[4], s_gp[5] - f[5], s_gp[6] - f[6]);
+                    const double qp = qlen2(s_gp[3] + f[3], s_gp[4] + f[4], s_gp[5] + f[5], s_gp[6] + f[6]);
+                    prim = (e_pos + (qm < qp ? qm : qp) * (s_gp[7] * s_gp[7])) * wsq0;
+                    // running top-2 of this lane on the integer keys of the fitness (the order the selection uses, NaN last): a lane
+                    // meets its children in increasing position order, so the strict < keeps the earlier one on ties - branch-free
+                    const uint64_t key = c < C ? fast_fitness_key(prim) : FAST_KEY_NONE;
+                    const uint32_t pk = (uint32_t)c * 512u + (uint32_t)c;
+                    const bool lt1 = key < k1, lt2 = key < k2;
+                    k2 = lt1 ? k1 : (lt2 ? key : k2);
+                    q2 = lt1 ? q1 : (lt2 ? pk : q2);
+                    k1 = lt1 ? key : k1;
+                    q1 = lt1 ? pk : q1;
+                    continue;
+                }
                 if(GSPEC == 1)
                     prim += link_goal_value(G_POSE, s_gp, F[k][0]) * wsq0;
                 else
@@ -733,7 +783,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 }
             }
         }
-        if(!P.has_secondary)
+        if(!P.has_secondary && !LEAN)
         {
             k1 = q1 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b1);
             k2 = q2 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b2);
@@ -900,12 +950,30 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
 
 typedef void (*EvolveFastKernel)(const DProblem*, DState, int, const double*);
 
+// name of the kernel instantiation the last select_* call of this thread returned (bench.py's roofline.kernel)
+inline const char*& selected_kernel_name()
+{
+    static thread_local const char* name = "";
+    return name;
+}
+#define BIOIK_NAMED_AS(TYPE, ...) (selected_kernel_name() = #__VA_ARGS__, (TYPE)__VA_ARGS__)
+
 // picks the instantiation for (tips, population, goals); returns nullptr if the generic kernel must be used
 // *lanes_per_task (if given) receives the lane-group width of the returned kernel: the launch has 32 / width tasks per warp
 inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap = 8, int* lanes_per_task = nullptr, int lpt_want = 16)
 {
     const int T = P.T;
     if(lanes_per_task) *lanes_per_task = 32;
+#ifdef BIOIK_SLIM
+#ifndef BIOIK_X_CH
+#define BIOIK_X_CH 4
+#endif
+#ifndef BIOIK_X_LPT
+#define BIOIK_X_LPT 16
+#endif
+    if(lanes_per_task) *lanes_per_task = BIOIK_X_LPT;
+    return BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, BIOIK_X_CH, 1, false, 7, false, BIOIK_X_LPT>);
+#else
     if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
     if(P.n_quat > 0) return nullptr; // quaternion genes are renormalised after the mutation (couples four genes): generic kernel
     const bool J = P.n_joint_goals > 0;
@@ -913,7 +981,7 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     int cpl = mtab_row(C) / 32; // 1, 2, 4 or 8
     if(cpl > ch_cap) cpl = ch_cap; // experiment knob: smaller register blocks (more chunks, fewer registers)
     if(J && cpl > 2) cpl = 2;      // joint-space accumulators on top of the frame accumulators: blocks of 4 spill (cfg4: 29.5 vs 21.8 ms per pass)
-#define BIOIK_PICK(TT, CC) (J ? (EvolveFastKernel)k_evolve_fast<TT, CC, 0, true> : (EvolveFastKernel)k_evolve_fast<TT, CC, 0, false>)
+#define BIOIK_PICK(TT, CC) (J ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<TT, CC, 0, true>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<TT, CC, 0, false>))
     if(single_pose && (P.n == 7 || P.n == 6) && ch_cap >= 8)
     {
         // lane groups: LPT lanes per task, R / (LPT * CH) chunks of CH children per lane.  R >= 128: 8, 16 or 32 lanes as wanted,
@@ -924,19 +992,20 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
         if(R == 32) lpt = lanes_per_task ? 16 : 32;
         if(lanes_per_task) *lanes_per_task = lpt;
 #define BIOIK_PICK_LG(NN)                                                                                                                                              \
-    (R == 32 ? (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false, NN, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>)                          \
-             : (lpt == 8 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN, false, 8> : (lpt == 16 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN, false, 16> : (EvolveFastKernel)k_evolve_fast<1, 4, 1, false, NN>)))
+    (R == 32 ? (lpt == 16 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 2, 1, false, NN, false, 16>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 1, 1, false>))                          \
+             : (lpt == 8 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 4, 1, false, NN, false, 8>) : (lpt == 16 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 4, 1, false, NN, false, 16>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 4, 1, false, NN>))))
         return P.n == 7 ? BIOIK_PICK_LG(7) : BIOIK_PICK_LG(6);
 #undef BIOIK_PICK_LG
     }
-    if(single_pose) return cpl >= 3 ? (EvolveFastKernel)k_evolve_fast<1, 4, 1, false> : (cpl == 2 ? (EvolveFastKernel)k_evolve_fast<1, 2, 1, false> : (EvolveFastKernel)k_evolve_fast<1, 1, 1, false>);
+    if(single_pose) return cpl >= 3 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 4, 1, false>) : (cpl == 2 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 2, 1, false>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 1, 1, false>));
     if(T == 1) return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));
     if(T == 2) return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1); // two tips still fit the gene-major register block (cfg3: 9.9 vs 10.1 ms per pass)
     // three or more tips: the tip-major form (one tip's accumulators at a time, so the register block does not depend on T; cfg5: 54.7 vs 57.6 ms)
-#define BIOIK_PICK_TM(CC) (J ? (EvolveFastKernel)k_evolve_fast<1, CC, 0, true, 0, true> : (EvolveFastKernel)k_evolve_fast<1, CC, 0, false, 0, true>)
+#define BIOIK_PICK_TM(CC) (J ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, CC, 0, true, 0, true>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, CC, 0, false, 0, true>))
     return cpl >= 3 ? BIOIK_PICK_TM(4) : (cpl == 2 ? BIOIK_PICK_TM(2) : BIOIK_PICK_TM(1));
 #undef BIOIK_PICK_TM
 #undef BIOIK_PICK
+#endif
 }
 
 } // namespace bioik

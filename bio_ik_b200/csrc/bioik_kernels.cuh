@@ -47,6 +47,7 @@ struct DState
     // shared lookup tables / schedules
     const double* uniform;     // [2^23]
     const double* gauss;       // [2^23]
+    double gauss_absmax;       // max |gauss[i]| over the table: bounds every mutation term (clamp elision in the generation kernel)
     const int32_t* gauss_off;  // [total_steps*2*gens] slab start of each reproduce() call
     const uint8_t* rate_exp;   // [total_steps*2*gens][C-2] fast_random_index(16) per child
 };

@@ -275,8 +275,12 @@ typedef void (*MemeticGroupKernel)(const DProblem, DState, int);
 
 inline MemeticGroupKernel select_memetic_group(int W, bool stale = false)
 {
+#ifdef BIOIK_SLIM
+    return (MemeticGroupKernel)k_memetic_group<8>;
+#else
     if(stale) return W == 8 ? (MemeticGroupKernel)k_memetic_group<8, true> : (W == 16 ? (MemeticGroupKernel)k_memetic_group<16, true> : (MemeticGroupKernel)k_memetic_group<32, true>);
     return W == 8 ? (MemeticGroupKernel)k_memetic_group<8> : (W == 16 ? (MemeticGroupKernel)k_memetic_group<16> : (MemeticGroupKernel)k_memetic_group<32>);
+#endif
 }
 
 // the reference-quirk mode changes something only if some gene cannot move some tip

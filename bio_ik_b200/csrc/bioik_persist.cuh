@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(32 * PERSIST_WARPS, 4) k_persist(BIOIK_PROBLEM
         else
         {
             const int g = (int)(item & 0xFFFFFFFFu), phases = (int)(item >> 56);
+#ifndef BIOIK_X_NOSERIAL // timing experiment only (wrong results): serial items do nothing but release the next evolve items
             serial_tasks<32, DS, FS>(P, S, step, phases, ser, wl, 2 * PERSIST_GROUP_QUERIES * g + wl);
+#endif
             __threadfence();
             __syncwarp();
             const int next = phases == PH_PREPARE ? step : step + 1; // a PREPARE item opens its own step
@@ -249,9 +251,13 @@ inline PersistKernel select_persist(const DProblem& P, int C, bool* delta_smem, 
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && P.T == 1);
     if(!single_pose || !has_unrolled_memetic(P) || P.n_quat > 0 || C > 32 * FAST_MAX_CPL) return nullptr;
     *delta_smem = true, *frames_smem = false;
+#ifdef BIOIK_SLIM
+    return BIOIK_NAMED_AS(PersistKernel, k_persist<1, 4, 1, false, 7, false, 16, true, false>);
+#else
     if(mtab_row(C) == 32) // population <= 34 (the reference's 18): register blocks of 2
-        return P.n == 7 ? (PersistKernel)k_persist<1, 2, 1, false, 7, false, 16, true, false> : (PersistKernel)k_persist<1, 2, 1, false, 6, false, 16, true, false>;
-    return P.n == 7 ? (PersistKernel)k_persist<1, 4, 1, false, 7, false, 16, true, false> : (PersistKernel)k_persist<1, 4, 1, false, 6, false, 16, true, false>;
+        return P.n == 7 ? BIOIK_NAMED_AS(PersistKernel, k_persist<1, 2, 1, false, 7, false, 16, true, false>) : BIOIK_NAMED_AS(PersistKernel, k_persist<1, 2, 1, false, 6, false, 16, true, false>);
+    return P.n == 7 ? BIOIK_NAMED_AS(PersistKernel, k_persist<1, 4, 1, false, 7, false, 16, true, false>) : BIOIK_NAMED_AS(PersistKernel, k_persist<1, 4, 1, false, 6, false, 16, true, false>);
+#endif
 }
 
 } // namespace bioik

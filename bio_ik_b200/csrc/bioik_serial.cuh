@@ -618,6 +618,9 @@ typedef void (*SerialKernel)(const DProblem, DState, int, int);
 
 inline SerialKernel select_serial(const SerialPlan& pl)
 {
+#ifdef BIOIK_SLIM // experiment builds: the headline shape only (fast compile)
+    return (SerialKernel)k_serial<32, true, false>;
+#else
 #define BIOIK_SER(BS)                                                                                                            \
     (pl.delta_smem ? (pl.frames_smem ? (SerialKernel)k_serial<BS, true, true> : (SerialKernel)k_serial<BS, true, false>) \
                    : (pl.frames_smem ? (SerialKernel)k_serial<BS, false, true> : (SerialKernel)k_serial<BS, false, false>))
@@ -628,6 +631,7 @@ inline SerialKernel select_serial(const SerialPlan& pl)
     default: return BIOIK_SER(32);
     }
 #undef BIOIK_SER
+#endif
 }
 
 } // namespace bioik

@@ -50,3 +50,53 @@ def solve_sharded(solve_fn, n_vars, goal_params, seeds, rng_seeds, steps, early_
     dist.all_gather_into_tensor(gathered, slab)
     # ranks own consecutive `per`-row blocks, so the gathered slab is already in query order
     return unpack_slab(gathered.cpu().numpy(), n_vars, B)
+
+
+class DeviceShardedSolver:
+    """Device-resident form of the same scheme for throughput runs (bench.py): every rank owns a shard of B queries whose
+    inputs already live in its HBM; one pass = bioik_solve_batch_device on the shard, bioik_pack_results_device into the
+    [B][n_vars + 3] slab and - world > 1 - ONE all_gather_into_tensor of the slabs (NCCL over NVLink), all enqueued on `stream`."""
+
+    def __init__(self, solver, B, device, stream):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.solver, self.B, self.stream = solver, B, stream
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        n_vars = solver.robot_model.n_vars
+        self.sol = torch.empty((B, n_vars), dtype=torch.float64, device=device)
+        self.fit = torch.empty(B, dtype=torch.float64, device=device)
+        self.succ = torch.empty(B, dtype=torch.int32, device=device)
+        self.steps = torch.empty(B, dtype=torch.int32, device=device)
+        self.slab = torch.empty((B, n_vars + 3), dtype=torch.float64, device=device)
+        self.gathered = torch.empty((self.world * B, n_vars + 3), dtype=torch.float64, device=device) if self.world > 1 else self.slab
+
+    def solve(self, d_goal_params, d_seeds, d_rng_seeds, steps, early_exit=False):
+        """d_*: torch tensors on this rank's device.  Returns the gathered slab [world * B][n_vars + 3] (not synchronised)."""
+        s, st = self.solver, self.stream.cuda_stream
+        s.solve_batch_device(self.B, d_goal_params.data_ptr(), d_seeds.data_ptr(), d_rng_seeds.data_ptr(), steps, early_exit, self.sol.data_ptr(), self.fit.data_ptr(), self.succ.data_ptr(), self.steps.data_ptr(),
+                             stream=st)
+        s.pack_results_device(self.B, self.sol.data_ptr(), self.fit.data_ptr(), self.succ.data_ptr(), self.steps.data_ptr(), self.slab.data_ptr(), stream=st)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self.slab)
+        return self.gathered
+
+    def solve_host(self, goal_params, seeds, rng_seeds, steps, out, early_exit=False):
+        """The host-buffer path of one rank (bioik_solve_batch: H2D + solve + D2H), then the gather of the result slabs: the
+        rank's results go back to the device slab, one all-gather, and every rank reads the full slab into `out["gathered"]`
+        (pinned).  world == 1: just the host call."""
+        res = self.solver.solve_batch(goal_params, seeds, rng_seeds, steps, early_exit=early_exit, out=out)
+        if self.world > 1:
+            torch = self.torch
+            n_vars = self.solver.robot_model.n_vars
+            host_slab = out["slab"]
+            host_slab[:, :n_vars] = torch.from_numpy(res["solutions"])
+            host_slab[:, n_vars] = torch.from_numpy(res["fitness"])
+            host_slab[:, n_vars + 1] = torch.from_numpy(res["success"]).to(torch.float64)
+            host_slab[:, n_vars + 2] = torch.from_numpy(res["steps"]).to(torch.float64)
+            with torch.cuda.stream(self.stream):
+                self.slab.copy_(host_slab, non_blocking=True)
+                self.dist.all_gather_into_tensor(self.gathered, self.slab)
+                out["gathered"].copy_(self.gathered, non_blocking=True)
+            self.stream.synchronize()
+        return res

@@ -133,6 +133,13 @@ class IKSolver:
         """Same with raw device pointers (ints); enqueues on `stream` (or the context stream), no sync."""
         self._check(self.lib.bioik_solve_batch_device(self._ctx, B, d_goal_params, d_seeds, d_rng_seeds, steps, int(early_exit), d_solutions, d_fitness, d_success, d_steps, stream))
 
+    def pack_results_device(self, B, d_solutions, d_fitness, d_success, d_steps, d_slab, stream=None):
+        """[B][n_vars + 3] float64 slab solution | fitness | success | steps from the device outputs of solve_batch_device"""
+        self._check(self.lib.bioik_pack_results_device(self._ctx, B, d_solutions, d_fitness, d_success, d_steps, d_slab, stream))
+
+    def kernel_name(self):
+        return self.lib.bioik_kernel_name(self._ctx).decode()
+
     def synchronize(self):
         self._check(self.lib.bioik_synchronize(self._ctx))
 

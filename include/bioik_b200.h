@@ -275,6 +275,16 @@ int bioik_step(bioik_ctx* ctx, int32_t nsteps, int32_t* out_active);
 int bioik_get_solution(bioik_ctx* ctx, int32_t wrap, double* out_solutions, double* out_fitness, int32_t* out_success,
                        int32_t* out_island, int32_t* out_steps);
 
+/* The result slab of a multi-GPU gather (one all-gather of the per-GPU results per solve round): packs the four
+ * device-resident outputs of bioik_solve_batch_device into d_slab [B][n_vars + 3] = solution | fitness | success | steps
+ * (all float64) on `cuda_stream`, not synchronised.  bio_ik_b200/distributed.py hands that slab to NCCL. */
+int bioik_pack_results_device(bioik_ctx* ctx, int32_t B, const double* d_solutions, const double* d_fitness,
+                              const int32_t* d_success, const int32_t* d_steps, double* d_slab, void* cuda_stream);
+
+/* Template instantiation of the kernel that bioik_kernel_time reports as the generation kernel for the solve shape last used
+ * (e.g. "k_persist<1, 4, 1, false, 7, false, 16, true, false>"); "" before the first solve. */
+const char* bioik_kernel_name(const bioik_ctx* ctx);
+
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 int64_t bioik_launch_count(const bioik_ctx* ctx);
 

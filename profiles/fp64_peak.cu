@@ -34,10 +34,16 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 
-// MODE 0: DFMA only; 1: DADD only; 2: generation-kernel mix per 13 instructions: 5 DFMA, 4 DADD, 2 DMUL, 2 DSETP(+select)
+// MODE 0: DFMA only; 1: DADD only; 2: generation-kernel mix per 13 instructions: 5 DFMA, 4 DADD, 2 DMUL, 2 DSETP(+select);
+// MODE 3 / 4: one DFMA + one / two independent 32-bit integer multiply-adds per step (does an FP64 instruction leave its second
+// issue cycle to another pipe, or does it hold the dispatch port for both cycles?)
 template <int ILP, int MODE> __global__ void __launch_bounds__(256) k_chains(double* out, int iters, double a, double b, unsigned long long* clk)
 {
     double acc[ILP];
+    unsigned iacc[ILP], jacc[ILP];
+#pragma unroll
+    for(int k = 0; k < ILP; k++) iacc[k] = threadIdx.x + k, jacc[k] = threadIdx.x * 3 + k;
+    const unsigned im = (unsigned)iters | 1u, ia = (unsigned)(a * 1e6) | 1u;
 #pragma unroll
     for(int k = 0; k < ILP; k++) acc[k] = (double)(threadIdx.x + k) * 1e-3;
     const long long c0 = clock64();
@@ -54,6 +60,12 @@ template <int ILP, int MODE> __global__ void __launch_bounds__(256) k_chains(dou
                     acc[k] = __fma_rn(acc[k], a, b);
                 else if(MODE == 1)
                     acc[k] = __dadd_rn(acc[k], b);
+                else if(MODE == 3 || MODE == 4)
+                {
+                    acc[k] = __fma_rn(acc[k], a, b);
+                    iacc[k] = iacc[k] * im + ia; // IMAD: integer pipe, independent of the FP64 chain
+                    if(MODE == 4) jacc[k] = jacc[k] * ia + im;
+                }
                 else
                 {
                     // 13 FP64-pipe instructions
@@ -80,7 +92,7 @@ template <int ILP, int MODE> __global__ void __launch_bounds__(256) k_chains(dou
     const unsigned long long t1 = gtimer();
     double s = 0;
 #pragma unroll
-    for(int k = 0; k < ILP; k++) s += acc[k];
+    for(int k = 0; k < ILP; k++) s += acc[k] + (double)(iacc[k] ^ jacc[k]);
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
     if(threadIdx.x == 0)
     {
@@ -122,8 +134,8 @@ template <int ILP, int MODE> int run(const char* name, int sms, int blocks_per_s
     double cyc = 0, ns = 0;
     for(int b = 0; b < blocks; b++) cyc += (double)clk[2 * b], ns += (double)clk[2 * b + 1];
     const double sm_mhz = cyc / ns * 1e3;
-    const double per_thread_inst = (double)iters * 8 * ILP * (MODE == 2 ? 13 : 1);
-    const double flop_per_inst = MODE == 0 ? 2.0 : (MODE == 1 ? 1.0 : (5 * 2 + 4 + 2 + 0) / 13.0);
+    const double per_thread_inst = (double)iters * 8 * ILP * (MODE == 2 ? 13 : 1); // FP64 instructions (MODE 3 / 4: the DFMAs; the integer ops ride along)
+    const double flop_per_inst = (MODE == 0 || MODE >= 3) ? 2.0 : (MODE == 1 ? 1.0 : (5 * 2 + 4 + 2 + 0) / 13.0);
     const double total_inst_thread = per_thread_inst * blocks * threads;
     const double tflops = total_inst_thread * flop_per_inst / (best * 1e-3) / 1e12;
     const double warp_inst = total_inst_thread / 32.0;
@@ -158,10 +170,12 @@ int main(int argc, char** argv)
     rc |= run<8, 0>("dfma", sms, 8, iters, st, d_out, d_clk, res);
     rc |= run<8, 1>("dadd", sms, 4, iters, st, d_out, d_clk, res);
     rc |= run<4, 2>("mix_5fma_4add_2mul_2setp", sms, 4, iters / 4, st, d_out, d_clk, res);
+    rc |= run<8, 3>("dfma_plus_1_imad", sms, 4, iters, st, d_out, d_clk, res);
+    rc |= run<8, 4>("dfma_plus_2_imad", sms, 4, iters, st, d_out, d_clk, res);
     if(rc) return rc;
     double peak = 0, peak_mhz = 0, peak_ipc = 0;
     for(auto& r : res)
-        if(r.name[1] == 'f' && r.tflops > peak) peak = r.tflops, peak_mhz = r.sm_mhz, peak_ipc = r.inst_per_cycle_smsp;
+        if(r.name[1] == 'f' && r.name[4] == 0 && r.tflops > peak) peak = r.tflops, peak_mhz = r.sm_mhz, peak_ipc = r.inst_per_cycle_smsp;
     printf("{\"device\": \"%s\", \"sm_count\": %d, \"fp64_tflops\": %.4f, \"sm_mhz_during_peak\": %.1f, \"dfma_warp_inst_per_cycle_per_smsp\": %.4f,\n", prop.name, sms, peak, peak_mhz, peak_ipc);
     printf(" \"nominal_tflops_at_that_clock\": %.4f, \"method\": \"independent DFMA chains, CUDA events on the launch stream, best of 5 after 3 warm-ups; clock = clock64/globaltimer inside the launch\",\n",
            sms * 64.0 * 2.0 * peak_mhz * 1e6 / 1e12);

@@ -248,6 +248,8 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
     S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.carry = carry.data(), S.cancel = nullptr, S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();
     S.uniform = hostsim_tables(cfg->table_seed, 0), S.gauss = hostsim_tables(cfg->table_seed, 1), S.gauss_off = go.data(), S.rate_exp = re.data();
+    S.gauss_absmax = 0;
+    for(size_t i = 0; i < (size_t)1 << 23; i++) S.gauss_absmax = std::max(S.gauss_absmax, std::fabs(S.gauss[i]));
     const int TPB = 128;
     int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
     int evolve_lpt = 32;
