@@ -15,8 +15,8 @@
 // seeds its islands from its thread_index.
 //
 // Only public interfaces of the reference are used (IKBase, Problem::GoalInfo, the goal classes' getters, moveit::core::RobotModel).
-// Goals without a closed form on the device (TouchGoal, JointFunctionGoal, LinkFunctionGoal, BalanceGoal without masses in
-// BioikRobot) raise the reference's ERROR(): keep mode=bio2_memetic for those queries.
+// Goals without a closed form on the device (TouchGoal, JointFunctionGoal, LinkFunctionGoal) raise the reference's ERROR():
+// keep mode=bio2_memetic for those queries.
 #include "ik_base.h"
 
 #include <bio_ik/goal_types.h>
@@ -35,7 +35,7 @@ template <int memetic> struct IKEvolution2B200 : IKBase
     struct RobotTable
     {
         std::vector<int32_t> parent, jtype, first_var, mimic, bounded;
-        std::vector<double> origin, axis, mfac, moff, vmin, vmax, vvel;
+        std::vector<double> origin, axis, mfac, moff, vmin, vmax, vvel, mass, com;
     };
     RobotTable table;
     bioik_ctx* ctx = nullptr;
@@ -84,6 +84,13 @@ template <int memetic> struct IKEvolution2B200 : IKBase
             table.mimic.push_back(joint->getMimic() ? (int32_t)joint->getMimic()->getChildLinkModel()->getLinkIndex() : -1);
             table.mfac.push_back(joint->getMimicFactor());
             table.moff.push_back(joint->getMimicOffset());
+            // URDF inertial, as BalanceGoal::describe reads it (src/goal_types.cpp:236-250)
+            double mass = 0, cx = 0, cy = 0, cz = 0;
+            if(m.getURDF())
+                if(auto link_urdf = m.getURDF()->getLink(link->getName()))
+                    if(link_urdf->inertial) mass = link_urdf->inertial->mass, cx = link_urdf->inertial->origin.position.x, cy = link_urdf->inertial->origin.position.y, cz = link_urdf->inertial->origin.position.z;
+            table.mass.push_back(mass);
+            table.com.insert(table.com.end(), {cx, cy, cz});
         }
         for(auto& name : m.getVariableNames())
         {
@@ -104,6 +111,7 @@ template <int memetic> struct IKEvolution2B200 : IKBase
         r.link_origin = table.origin.data(), r.joint_axis = table.axis.data();
         r.joint_mimic = table.mimic.data(), r.joint_mimic_factor = table.mfac.data(), r.joint_mimic_offset = table.moff.data();
         r.var_min = table.vmin.data(), r.var_max = table.vmax.data(), r.var_bounded = table.bounded.data(), r.var_max_velocity = table.vvel.data();
+        r.link_mass = table.mass.data(), r.link_com = table.com.data();
         // the constants src/ik_evolution_2.cpp hard-codes: 2 + 16 children (:137-138,182), 8 generations per step (16 without the
         // memetic stage, :349-351), 8 line-search iterations (:453); the lookup tables are seeded like Random(p.random_seed)
         BioikSolverCfg cfg;
@@ -179,8 +187,10 @@ template <int memetic> struct IKEvolution2B200 : IKBase
             g.type = BIOIK_GOAL_MINIMAL_DISPLACEMENT;
         else if(auto* x = dynamic_cast<const JointVariableGoal*>(goal))
             g.type = BIOIK_GOAL_JOINT_VARIABLE, g.var = (int32_t)params.robot_model->getVariableIndex(x->getVariableName()), p[0] = x->getVariablePosition();
+        else if(auto* x = dynamic_cast<const BalanceGoal*>(goal))
+            g.type = BIOIK_GOAL_BALANCE, put3(p, x->getTarget()), put3(p + 3, x->getAxis()); // its links: every link with mass, already tips of the problem
         else
-            ERROR("goal class has no device implementation: keep a CPU solver mode for this query"); // Touch, JointFunction, LinkFunction, Balance
+            ERROR("goal class has no device implementation: keep a CPU solver mode for this query"); // Touch, JointFunction, LinkFunction
         return g;
     }
 

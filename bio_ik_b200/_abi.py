@@ -21,7 +21,7 @@ JOINT_VARS = {JOINT_FIXED: 0, JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_FLOAT
 # goal types (include/bio_ik/goal_types.h)
 (GOAL_POSITION, GOAL_ORIENTATION, GOAL_POSE, GOAL_LOOK_AT, GOAL_MAX_DISTANCE, GOAL_MIN_DISTANCE, GOAL_LINE,
  GOAL_PLANE, GOAL_AVOID_JOINT_LIMITS, GOAL_CENTER_JOINTS, GOAL_REGULARIZATION, GOAL_MINIMAL_DISPLACEMENT,
- GOAL_JOINT_VARIABLE, GOAL_SIDE, GOAL_DIRECTION, GOAL_CONE) = range(1, 17)
+ GOAL_JOINT_VARIABLE, GOAL_SIDE, GOAL_DIRECTION, GOAL_CONE, GOAL_BALANCE) = range(1, 18)
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -36,6 +36,7 @@ class BioikRobot(C.Structure):
         ("link_origin", c_double_p), ("joint_axis", c_double_p),
         ("joint_mimic", c_int32_p), ("joint_mimic_factor", c_double_p), ("joint_mimic_offset", c_double_p),
         ("var_min", c_double_p), ("var_max", c_double_p), ("var_bounded", c_int32_p), ("var_max_velocity", c_double_p),
+        ("link_mass", c_double_p), ("link_com", c_double_p),
     ]
 
 

@@ -81,6 +81,7 @@ struct bioik_ctx
     SerialKernel serial = nullptr;
     int sm_count = 148;
     bool force_generic = false; // BIOIK_FORCE_GENERIC=1: always use the generic generation kernel (tests)
+    bool generic_now = false;   // the solve in flight runs the generic kernels (forced, or a problem shape the fused kernels do not take)
 
     // state
     int capB = 0;
@@ -406,7 +407,9 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     R.B = B;
     R.next_step = 0;
     R.evolve_lpt = 32;
-    R.fast = ctx->force_generic ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &R.evolve_lpt, ctx->lpt_want);
+    // more than 8 tips (BalanceGoal: one per link with mass): the per-task shared-memory plans of the fused kernels do not apply
+    ctx->generic_now = ctx->force_generic || P.T > 8 || P.n_balance > 0;
+    R.fast = ctx->generic_now ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &R.evolve_lpt, ctx->lpt_want);
     R.dominant = R.fast ? selected_kernel_name() : "k_evolve";
     const int warps_per_block = BIOIK_EVOLVE_WPB;
     if(R.fast)
@@ -424,7 +427,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     const int TPB = 128;
     k_init<<<(B + TPB - 1) / TPB, TPB, 0, st>>>(ctx->dP, S);
     if((rc = check_launch(ctx, "k_init")) != BIOIK_OK) return rc;
-    if(!ctx->force_generic)
+    if(!ctx->generic_now)
     {
         // production path: k_evolve_fast (or k_evolve for shapes without a fast instantiation) + the fused k_serial
         ctx->splan = make_serial_plan(P, 2 * B, ctx->sm_count);
@@ -530,7 +533,7 @@ int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
     const DProblem& P = ctx->hP;
     const int B = S.B, TPB = 128, warps_per_block = BIOIK_EVOLVE_WPB;
     const int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
-    if(!ctx->force_generic && R.persist)
+    if(!ctx->generic_now && R.persist)
     {
         // One launch per burst of steps.  With the driver's `finished` flag among islands that span several serial groups
         // (early_exit 2) the bursts end at the 4-step tests: a success recorded by one group must not be seen by a group that is
@@ -574,7 +577,7 @@ int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
             a = b;
         }
     }
-    else if(!ctx->force_generic)
+    else if(!ctx->generic_now)
     {
         if(!R.prepared)
         {

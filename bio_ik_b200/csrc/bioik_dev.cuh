@@ -62,7 +62,7 @@ namespace bioik
 constexpr int MAX_VARS = 64;   // robot variables
 constexpr int MAX_GENES = 48;  // active variables
 constexpr int MAX_SLOTS = 96;  // links in the FK schedule
-constexpr int MAX_TIPS = 8;
+constexpr int MAX_TIPS = 24; // BalanceGoal makes every link with mass a tip (src/goal_types.cpp:251)
 constexpr int MAX_GOALS = 24;
 constexpr int GOAL_NPARAM = 12;
 constexpr double DBLMAX = 1.7976931348623157e308;
@@ -70,7 +70,7 @@ constexpr double DBLMAX = 1.7976931348623157e308;
 enum JointType { J_FIXED = 0, J_REVOLUTE = 1, J_PRISMATIC = 2, J_FLOATING = 3, J_PLANAR = 4 };
 enum GoalType {
     G_POSITION = 1, G_ORIENTATION, G_POSE, G_LOOK_AT, G_MAX_DISTANCE, G_MIN_DISTANCE, G_LINE, G_PLANE, G_AVOID_JOINT_LIMITS,
-    G_CENTER_JOINTS, G_REGULARIZATION, G_MINIMAL_DISPLACEMENT, G_JOINT_VARIABLE, G_SIDE, G_DIRECTION, G_CONE
+    G_CENTER_JOINTS, G_REGULARIZATION, G_MINIMAL_DISPLACEMENT, G_JOINT_VARIABLE, G_SIDE, G_DIRECTION, G_CONE, G_BALANCE
 };
 
 // ---------------------------------------------------------------------------
@@ -120,6 +120,12 @@ struct DProblem
     int32_t n_quat;               // floating joints among the genes: quat_gene[k] = gene of rot_x, the next three genes are rot_y, rot_z, rot_w (ik_evolution_2.cpp:118-126)
     int32_t quat_gene[MAX_GENES / 4];
     int32_t wrap_gene[MAX_GENES]; // 1: the plugin's angle wrap applies (revolute variable, robot without mimic joints; kinematics_plugin.cpp:583-584)
+    // BalanceGoal::balance_infos (src/goal_types.cpp:236-259): the links with mass in link order - their tip index, inertial origin
+    // and mass / total mass
+    int32_t n_balance;
+    int32_t balance_tip[MAX_TIPS];
+    double balance_center[MAX_TIPS][3];
+    double balance_weight[MAX_TIPS];
 };
 
 // ---------------------------------------------------------------------------
@@ -689,17 +695,37 @@ template <class AP, class AT, class AX, class AS> BIOIK_HD double goal_value(con
         return len2(p[3] - v.x, p[4] - v.y, p[5] - v.z);
     }
     case G_CONE: return cone_goal_value(p, f);
+    case G_BALANCE: // src/goal_types.cpp:261-272 (tf2 operator order: c * w component-wise, then +=; dot = x x' + y y' + z z')
+    {
+        double cx = 0.0, cy = 0.0, cz = 0.0;
+        for(int i = 0; i < P.n_balance; i++)
+        {
+            AT fr = tips + 7 * P.balance_tip[i];
+            V3 c = quat_mul_vec(Q4{fr[3], fr[4], fr[5], fr[6]}, V3{P.balance_center[i][0], P.balance_center[i][1], P.balance_center[i][2]});
+            c.x += fr[0]; c.y += fr[1]; c.z += fr[2];
+            const double w = P.balance_weight[i];
+            cx += c.x * w; cy += c.y * w; cz += c.z * w;
+        }
+        cx -= p[0]; cy -= p[1]; cz -= p[2];
+        const double k = p[3] * cx + p[4] * cy + p[5] * cz; // axis_.dot(center)
+        cx -= p[3] * k; cy -= p[4] * k; cz -= p[5] * k;
+        return len2(cx, cy, cz);
+    }
     default: return 0.0;
     }
 }
 
 // IKBase::null_tip_frames (src/ik_base.h:135,160,163): what secondary goals receive instead of
 // tip frames.  Uninitialised memory in the reference; identity frames here and in the oracle.
+// (an identity frame per tip)
+#define BIOIK_ID7 0, 0, 0, 0, 0, 0, 1
+#define BIOIK_ID7x8 BIOIK_ID7, BIOIK_ID7, BIOIK_ID7, BIOIK_ID7, BIOIK_ID7, BIOIK_ID7, BIOIK_ID7, BIOIK_ID7
 #ifdef BIOIK_HOSTSIM
-static const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+static const double NULL_TIPS[MAX_TIPS * 7] = {BIOIK_ID7x8, BIOIK_ID7x8, BIOIK_ID7x8};
 #else
-static __device__ const double NULL_TIPS[MAX_TIPS * 7] = {0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1};
+static __device__ const double NULL_TIPS[MAX_TIPS * 7] = {BIOIK_ID7x8, BIOIK_ID7x8, BIOIK_ID7x8};
 #endif
+static_assert(MAX_TIPS == 24, "NULL_TIPS lists 24 identity frames");
 
 template <class AP, class AT, class AX, class AS> BIOIK_HD double goal_fitness_t(const DProblem& P, int which, AP gp, AT tips, AX x, AS seed)
 {

@@ -975,6 +975,7 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     return BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, BIOIK_X_CH, 1, false, 7, false, BIOIK_X_LPT>);
 #else
     if(T < 1 || T > 8 || P.n_joint_goals > FAST_MAX_JOINT_GOALS || C > 32 * FAST_MAX_CPL) return nullptr;
+    if(P.n_balance > 0) return nullptr; // BalanceGoal reads every tip frame at once: the generic kernels evaluate it
     if(P.n_quat > 0) return nullptr; // quaternion genes are renormalised after the mutation (couples four genes): generic kernel
     const bool J = P.n_joint_goals > 0;
     const bool single_pose = (P.G == 1 && P.goals[0].type == G_POSE && !P.goals[0].secondary && T == 1);

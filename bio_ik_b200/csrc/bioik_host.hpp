@@ -25,6 +25,7 @@ struct HostRobot
     std::vector<int> parent, jtype, first_var, mimic;
     std::vector<double> origin, axis, mimic_factor, mimic_offset, var_min, var_max, var_vel;
     std::vector<int> var_bounded, var_joint;
+    std::vector<double> link_mass, link_com; // URDF inertials (BalanceGoal); empty = none
 };
 
 inline int var_count(int t)
@@ -67,6 +68,13 @@ inline int intake_robot(const BioikRobot* robot, HostRobot& R, std::string& err)
     R.var_max.assign(robot->var_max, robot->var_max + R.n_vars);
     R.var_bounded.assign(robot->var_bounded, robot->var_bounded + R.n_vars);
     R.var_vel.assign(robot->var_max_velocity, robot->var_max_velocity + R.n_vars);
+    R.link_mass.clear(), R.link_com.clear();
+    if(robot->link_mass)
+    {
+        R.link_mass.assign(robot->link_mass, robot->link_mass + R.n_links);
+        R.link_com.assign(3 * (size_t)R.n_links, 0.0);
+        if(robot->link_com) R.link_com.assign(robot->link_com, robot->link_com + 3 * (size_t)R.n_links);
+    }
     R.var_joint.assign(R.n_vars, -1);
     for(int l = 0; l < R.n_links; l++)
     {
@@ -134,7 +142,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
     memset(&P, 0, sizeof(P));
     if(p->n_tips < 1 || p->n_active < 1 || p->n_goals < 1) return host_fail(err, BIOIK_E_INVALID, "problem needs at least one tip, one active variable and one goal");
     if(p->n_tips > MAX_TIPS || p->n_active > MAX_GENES || p->n_goals > MAX_GOALS || R.n_vars > MAX_VARS)
-        return host_fail(err, BIOIK_E_LIMIT, "problem exceeds compiled-in capacity (tips<=8, genes<=48, goals<=24, vars<=64)");
+        return host_fail(err, BIOIK_E_LIMIT, "problem exceeds compiled-in capacity (tips<=24, genes<=48, goals<=24, vars<=64)");
     P.n_vars = R.n_vars;
     P.n = p->n_active;
     P.T = p->n_tips;
@@ -288,7 +296,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
     for(int g = 0; g < p->n_goals; g++)
     {
         const BioikGoal& bg = p->goals[g];
-        if(bg.type < BIOIK_GOAL_POSITION || bg.type > BIOIK_GOAL_CONE) return host_fail(err, BIOIK_E_UNSUPPORTED_GOAL, "goal type has no device implementation (callback / FCL goals stay on the CPU solver)");
+        if(bg.type < BIOIK_GOAL_POSITION || bg.type > BIOIK_GOAL_BALANCE) return host_fail(err, BIOIK_E_UNSUPPORTED_GOAL, "goal type has no device implementation (callback / FCL goals stay on the CPU solver)");
         DGoal& D = P.goals[g];
         D.type = bg.type;
         D.tip = bg.tip;
@@ -302,6 +310,30 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
             D.var_index = P.gene_of_var[bg.var] >= 0 ? P.gene_of_var[bg.var] : -1 - bg.var;
         }
         if(D.secondary) P.has_secondary = 1;
+        if(bg.type == BIOIK_GOAL_BALANCE && P.n_balance == 0)
+        {
+            // BalanceGoal::describe (src/goal_types.cpp:231-259): every link whose inertial has a positive mass, in link order, with
+            // weight = mass / total (total summed in the same order); each of them must be a tip link of the problem
+            double total = 0.0;
+            for(int l = 0; l < R.n_links && !R.link_mass.empty(); l++)
+            {
+                const double mass = R.link_mass[l];
+                if(!(mass > 0)) continue;
+                if(P.n_balance >= MAX_TIPS) return host_fail(err, BIOIK_E_LIMIT, "BalanceGoal: more than 24 links with mass");
+                if(slot_of_link[l] < 0) return host_fail(err, BIOIK_E_INVALID, "BalanceGoal: every link with mass must be a tip link of the problem");
+                int tip = -1;
+                for(int t = 0; t < p->n_tips; t++)
+                    if(p->tip_links[t] == l) tip = t;
+                if(tip < 0) return host_fail(err, BIOIK_E_INVALID, "BalanceGoal: every link with mass must be a tip link of the problem");
+                P.balance_tip[P.n_balance] = tip;
+                for(int k = 0; k < 3; k++) P.balance_center[P.n_balance][k] = R.link_com[3 * (size_t)l + k];
+                P.balance_weight[P.n_balance] = mass;
+                total += mass;
+                P.n_balance++;
+            }
+            if(P.n_balance == 0) return host_fail(err, BIOIK_E_INVALID, "BalanceGoal needs BioikRobot::link_mass (no link has mass)");
+            for(int i = 0; i < P.n_balance; i++) P.balance_weight[i] /= total;
+        }
         if(bg.type >= BIOIK_GOAL_AVOID_JOINT_LIMITS && bg.type <= BIOIK_GOAL_JOINT_VARIABLE) P.n_joint_goals++;
     }
     // thresholds (src/problem.cpp:90-95)

@@ -325,3 +325,33 @@ class LinkFunctionGoal(_HostOnlyGoal):
 
 class TouchGoal(_HostOnlyGoal):
     """src/goal_types.cpp:46-228 (FCL collision geometry)"""
+
+
+class BalanceGoal(Goal):
+    """goal_types.h:540-568, src/goal_types.cpp:231-272: the centre of mass - the mass-weighted mean of every link's inertial origin,
+    taken over the links whose URDF inertial has a positive mass - is pulled onto the line through `target` along `axis`.
+    describe() makes each of those links a goal link (in link order), so they all become tip links of the problem."""
+    type = _abi.GOAL_BALANCE
+
+    def __init__(self, target=(0, 0, 0), weight=1.0, axis=(0, 0, 1)):
+        super().__init__()
+        self.weight_ = float(weight)
+        self.target_, self.axis_ = _v3(target), _v3(axis)  # neither the constructor nor the setters normalise
+
+    def setTarget(self, t):
+        self.target_ = _v3(t)
+
+    def setAxis(self, a):
+        self.axis_ = _v3(a)
+
+    def getTarget(self):
+        return self.target_
+
+    def getAxis(self):
+        return self.axis_
+
+    def describe_links(self, robot_model):
+        return [l.name for l in robot_model.links if l.mass > 0]
+
+    def params(self):
+        return _pad(list(self.target_) + list(self.axis_))

@@ -60,12 +60,15 @@ struct RobotModel
         bool bounded = true;
         std::string mimic; // joint name
         double mimic_factor = 1, mimic_offset = 0;
+        double mass = 0;           // URDF inertial (BalanceGoal, src/goal_types.cpp:236-250)
+        double com[3] = {0, 0, 0}; // inertial origin in the link frame
     };
     std::vector<Link> links;
     std::vector<std::string> variable_names;
     std::vector<int32_t> link_parent, joint_type, joint_first_var, joint_mimic, var_bounded;
-    std::vector<double> link_origin, joint_axis, joint_mimic_factor, joint_mimic_offset, var_min, var_max, var_max_velocity;
+    std::vector<double> link_origin, joint_axis, joint_mimic_factor, joint_mimic_offset, var_min, var_max, var_max_velocity, link_mass, link_com;
     std::map<std::string, int> link_index, joint_index, variable_index;
+    static int variableCount(int joint_type) { return joint_type == BIOIK_JOINT_REVOLUTE || joint_type == BIOIK_JOINT_PRISMATIC ? 1 : (joint_type == BIOIK_JOINT_FLOATING ? 7 : (joint_type == BIOIK_JOINT_PLANAR ? 3 : 0)); }
 
     void addLink(const Link& l) { links.push_back(l); }
     // call once after all links were added (parents before children)
@@ -75,31 +78,44 @@ struct RobotModel
         for(size_t i = 0; i < links.size(); i++) link_index[links[i].name] = (int)i, joint_index[links[i].joint_name] = (int)i;
         link_parent.clear(), joint_type.clear(), joint_first_var.clear(), joint_mimic.clear(), link_origin.clear(), joint_axis.clear();
         joint_mimic_factor.clear(), joint_mimic_offset.clear(), var_min.clear(), var_max.clear(), var_bounded.clear(), var_max_velocity.clear();
+        link_mass.clear(), link_com.clear();
         for(auto& l : links)
         {
             if(!l.parent.empty() && !link_index.count(l.parent)) throw std::runtime_error("link not found " + l.parent);
             link_parent.push_back(l.parent.empty() ? -1 : link_index[l.parent]);
             joint_type.push_back(l.joint_type);
-            bool has_var = l.joint_type == BIOIK_JOINT_REVOLUTE || l.joint_type == BIOIK_JOINT_PRISMATIC;
-            if(l.joint_type == BIOIK_JOINT_FLOATING || l.joint_type == BIOIK_JOINT_PLANAR) throw std::runtime_error("floating / planar joints are not supported on the device yet");
-            joint_first_var.push_back(has_var ? (int)variable_names.size() : -1);
-            if(has_var)
+            const int cnt = variableCount(l.joint_type);
+            joint_first_var.push_back(cnt ? (int)variable_names.size() : -1);
+            auto addVariable = [&](const std::string& name, double lo, double hi, bool bounded) {
+                variable_index[name] = (int)variable_names.size();
+                variable_names.push_back(name);
+                var_min.push_back(lo), var_max.push_back(hi), var_bounded.push_back(bounded), var_max_velocity.push_back(l.velocity);
+            };
+            if(cnt == 1) addVariable(l.joint_name, l.lower, l.upper, l.bounded);
+            if(cnt == 7) // MoveIt FloatingJointModel: variable names and default bounds
             {
-                variable_index[l.joint_name] = (int)variable_names.size();
-                variable_names.push_back(l.joint_name);
-                var_min.push_back(l.lower), var_max.push_back(l.upper), var_bounded.push_back(l.bounded), var_max_velocity.push_back(l.velocity);
+                const char* names[7] = {"trans_x", "trans_y", "trans_z", "rot_x", "rot_y", "rot_z", "rot_w"};
+                for(int k = 0; k < 7; k++) addVariable(l.joint_name + "/" + names[k], k < 3 ? -1e308 : -1.0, k < 3 ? 1e308 : 1.0, k >= 3);
+            }
+            if(cnt == 3) // PlanarJointModel
+            {
+                const char* names[3] = {"x", "y", "theta"};
+                for(int k = 0; k < 3; k++) addVariable(l.joint_name + "/" + names[k], k < 2 ? -1e308 : -3.14159265358979323846, k < 2 ? 1e308 : 3.14159265358979323846, false);
             }
             for(double o : l.origin) link_origin.push_back(o);
             for(double a : l.axis) joint_axis.push_back(a);
             joint_mimic.push_back(l.mimic.empty() ? -1 : joint_index.at(l.mimic));
             joint_mimic_factor.push_back(l.mimic_factor), joint_mimic_offset.push_back(l.mimic_offset);
+            link_mass.push_back(l.mass);
+            for(double c : l.com) link_com.push_back(c);
         }
     }
     size_t getVariableCount() const { return variable_names.size(); }
     BioikRobot toABI() const
     {
-        BioikRobot r;
+        BioikRobot r{};
         r.n_links = (int32_t)links.size(), r.n_vars = (int32_t)variable_names.size();
+        r.link_mass = link_mass.data(), r.link_com = link_com.data();
         r.link_parent = link_parent.data(), r.joint_type = joint_type.data(), r.joint_first_var = joint_first_var.data();
         r.link_origin = link_origin.data(), r.joint_axis = joint_axis.data(), r.joint_mimic = joint_mimic.data();
         r.joint_mimic_factor = joint_mimic_factor.data(), r.joint_mimic_offset = joint_mimic_offset.data();
@@ -130,6 +146,13 @@ public:
     // flattened description: goal type, link name / variable name it refers to, parameter block
     virtual int type() const = 0;
     virtual std::string linkName() const { return ""; }
+    // every link the goal refers to (GoalContext::addLink in describe()); the first one is its tip.  Default: linkName()
+    virtual std::vector<std::string> linkNames(const struct RobotModel&) const
+    {
+        std::vector<std::string> r;
+        if(!linkName().empty()) r.push_back(linkName());
+        return r;
+    }
     virtual std::string variableName() const { return ""; }
     virtual void params(double* p) const { (void)p; }
 };
@@ -330,6 +353,30 @@ public:
     void params(double* p) const override { p[0] = variable_position; }
 };
 
+// goal_types.h:540-568, src/goal_types.cpp:231-272: the centre of mass over every link with a positive inertial mass is pulled onto
+// the line through `target` along `axis`; each of those links becomes a tip link of the problem (link order)
+class BalanceGoal : public Goal
+{
+    Vector3 target_{0, 0, 0}, axis_{0, 0, 1};
+
+public:
+    BalanceGoal() {}
+    BalanceGoal(const Vector3& target, double weight = 1.0) : target_(target) { weight_ = weight; }
+    const Vector3& getTarget() const { return target_; }
+    const Vector3& getAxis() const { return axis_; }
+    void setTarget(const Vector3& t) { target_ = t; }
+    void setAxis(const Vector3& a) { axis_ = a; }
+    int type() const override { return BIOIK_GOAL_BALANCE; }
+    std::vector<std::string> linkNames(const RobotModel& robot) const override
+    {
+        std::vector<std::string> r;
+        for(auto& l : robot.links)
+            if(l.mass > 0) r.push_back(l.name);
+        return r;
+    }
+    void params(double* p) const override { BIOIK_V3(p, 0, target_), BIOIK_V3(p, 3, axis_); }
+};
+
 // ---- Problem (src/problem.cpp:72-228): tips, active variables, flattened goals ---------------------------
 class Problem
 {
@@ -338,47 +385,66 @@ public:
     std::vector<BioikGoal> goals;
     double dpos = DBL_MAX, drot = DBL_MAX, dtwist = 1e-5;
 
-    void initialize(const RobotModel& robot, const JointModelGroup& group, const std::vector<const Goal*>& goal_list)
+    // fixed_joints: BioIKKinematicsQueryOptions::fixed_joints (joint names whose variables stay at the seed)
+    void initialize(const RobotModel& robot, const JointModelGroup& group, const std::vector<const Goal*>& goal_list, const std::vector<std::string>& fixed_joints = {})
     {
         tip_link_indices.clear(), active_variables.clear(), goals.clear();
         std::vector<int> link_tip(robot.links.size(), -1);
+        auto jointOfVariable = [&](int v) {
+            for(size_t l = 0; l < robot.links.size(); l++)
+                if(robot.joint_first_var[l] >= 0 && v >= robot.joint_first_var[l] && v < robot.joint_first_var[l] + RobotModel::variableCount(robot.links[l].joint_type)) return (int)l;
+            return -1;
+        };
+        auto isFixed = [&](int link) {
+            for(auto& f : fixed_joints)
+                if(link >= 0 && f == robot.links[link].joint_name) return true;
+            return false;
+        };
+        // src/problem.cpp:103-126: a fixed joint's variable stays out; otherwise the variable must belong to the joint group
         auto addActive = [&](const std::string& variable) {
             auto it = robot.variable_index.find(variable);
             if(it == robot.variable_index.end()) throw std::runtime_error("joint variable not found " + variable);
+            const int joint = jointOfVariable(it->second);
+            if(isFixed(joint)) return;
             for(int v : active_variables)
                 if(v == it->second) return;
+            bool in_group = false;
+            for(auto& jn : group.joint_names) in_group = in_group || (joint >= 0 && jn == robot.links[joint].joint_name);
+            if(!in_group) throw std::runtime_error("joint variable not found " + variable);
             active_variables.push_back(it->second);
         };
         for(const Goal* g : goal_list)
         {
             BioikGoal bg{};
             bg.type = g->type(), bg.secondary = g->isSecondary(), bg.weight = g->getWeight();
-            std::string ln = g->linkName();
-            if(!ln.empty())
+            bool first = true;
+            for(auto& ln : g->linkNames(robot))
             {
                 auto it = robot.link_index.find(ln);
                 if(it == robot.link_index.end()) throw std::runtime_error("link not found " + ln);
                 if(link_tip[it->second] < 0) link_tip[it->second] = (int)tip_link_indices.size(), tip_link_indices.push_back(it->second);
-                bg.tip = link_tip[it->second];
+                if(first) bg.tip = link_tip[it->second];
+                first = false;
             }
             std::string vn = g->variableName();
             if(!vn.empty()) addActive(vn), bg.var = robot.variable_index.at(vn);
             g->params(bg.p);
             goals.push_back(bg);
         }
-        // active variables from the active subtree (:191-204)
+        // active variables from the active subtree (:191-204): every variable of every used, non-mimic, non-fixed joint of the group
         std::vector<int> usage(robot.links.size(), 0);
         for(int tip : tip_link_indices)
             for(int l = tip; l >= 0; l = robot.link_parent[l]) usage[l] = 1;
         for(auto& jn : group.joint_names)
         {
             int l = robot.joint_index.at(jn);
-            if(usage[l] && robot.links[l].mimic.empty() && robot.joint_first_var[l] >= 0) addActive(robot.variable_names[robot.joint_first_var[l]]);
+            if(!usage[l] || !robot.links[l].mimic.empty() || isFixed(l)) continue;
+            for(int k = 0; k < RobotModel::variableCount(robot.links[l].joint_type); k++) addActive(robot.variable_names[robot.joint_first_var[l] + k]);
         }
     }
     BioikProblem toABI() const
     {
-        BioikProblem p;
+        BioikProblem p{};
         p.n_tips = (int32_t)tip_link_indices.size(), p.tip_links = tip_link_indices.data();
         p.n_active = (int32_t)active_variables.size(), p.active_vars = active_variables.data();
         p.n_goals = (int32_t)goals.size(), p.goals = goals.data();
@@ -392,6 +458,7 @@ class IKSolverB200
 {
     bioik_ctx* ctx_ = nullptr;
     size_t n_vars_ = 0;
+    int queries_ = 0;
 
     void check(int rc, const char* what)
     {
@@ -451,7 +518,8 @@ public:
     };
     // Q MoveIt-style queries, `islands` differently seeded runs each, reduced like IKParallel::solve (src/ik_parallel.h:218-258)
     // and angle-wrapped like the plugin (src/kinematics_plugin.cpp:580-611).  rng_seeds: [Q * islands].
-    IslandResult solveIslands(const std::vector<double>& goal_params, const std::vector<double>& seeds, int islands, const std::vector<uint32_t>& rng_seeds, int steps, bool early_exit = true, bool wrap = true)
+    // early_exit: 0 = every island runs `steps` steps, 1 = an island stops at its own success, 2 = the driver's `finished` flag among the islands
+    IslandResult solveIslands(const std::vector<double>& goal_params, const std::vector<double>& seeds, int islands, const std::vector<uint32_t>& rng_seeds, int steps, int early_exit = 2, bool wrap = true)
     {
         int Q = (int)(rng_seeds.size() / (size_t)islands);
         IslandResult r;
@@ -459,6 +527,26 @@ public:
         check(bioik_solve_islands(ctx_, Q, islands, goal_params.empty() ? nullptr : goal_params.data(), seeds.data(), rng_seeds.data(), steps, early_exit, wrap, r.solutions.data(), r.fitness.data(), r.success.data(),
                                   r.island.data(), r.steps.data()),
               "bioik_solve_islands");
+        return r;
+    }
+    // the reference's solver interface in its resumable form: IKBase::initialize / step / getSolution (src/ik_base.h:138-154) for
+    // Q queries x `islands` runs; the state stays on the device between the calls
+    void begin(const std::vector<double>& goal_params, const std::vector<double>& seeds, int islands, const std::vector<uint32_t>& rng_seeds, int max_steps = 0, int early_exit = 2)
+    {
+        queries_ = (int)(rng_seeds.size() / (size_t)islands);
+        check(bioik_begin(ctx_, queries_, islands, goal_params.empty() ? nullptr : goal_params.data(), seeds.data(), rng_seeds.data(), max_steps, early_exit), "bioik_begin");
+    }
+    int step(int nsteps = 1) // returns the number of runs that would execute a further step
+    {
+        int32_t active = 0;
+        check(bioik_step(ctx_, nsteps, &active), "bioik_step");
+        return active;
+    }
+    IslandResult getSolution(bool wrap = false)
+    {
+        IslandResult r;
+        r.solutions.resize((size_t)queries_ * n_vars_), r.fitness.resize(queries_), r.success.resize(queries_), r.island.resize(queries_), r.steps.resize(queries_);
+        check(bioik_get_solution(ctx_, wrap, r.solutions.data(), r.fitness.data(), r.success.data(), r.island.data(), r.steps.data()), "bioik_get_solution");
         return r;
     }
     std::vector<double> forwardKinematics(const std::vector<double>& variables, int n_tips)

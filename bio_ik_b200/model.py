@@ -25,7 +25,7 @@ class Link:
 
     def __init__(self, name, parent=None, joint_type=_abi.JOINT_FIXED, xyz=(0, 0, 0), rpy=(0, 0, 0), quat=None,
                  axis=(0, 0, 1), lower=0.0, upper=0.0, bounded=True, velocity=1.0, joint_name=None, mimic=None,
-                 mimic_factor=1.0, mimic_offset=0.0, var_lower=None, var_upper=None, var_bounded=None):
+                 mimic_factor=1.0, mimic_offset=0.0, var_lower=None, var_upper=None, var_bounded=None, mass=0.0, com=(0, 0, 0)):
         self.name = name
         self.parent = parent
         self.joint_type = joint_type
@@ -38,6 +38,8 @@ class Link:
         self.mimic_factor, self.mimic_offset = float(mimic_factor), float(mimic_offset)
         # per-variable bounds of multi-variable joints (floating: 7, planar: 3); None = the MoveIt defaults
         self.var_lower, self.var_upper, self.var_bounded = var_lower, var_upper, var_bounded
+        # URDF inertial (mass, centre of mass in the link frame): read only by BalanceGoal (src/goal_types.cpp:236-250)
+        self.mass, self.com = float(mass), tuple(float(v) for v in com)
 
 
 class RobotModel:
@@ -94,6 +96,8 @@ class RobotModel:
         a["var_max"] = np.array(vmax, dtype=np.float64)
         a["var_bounded"] = np.array(vb, dtype=np.int32)
         a["var_max_velocity"] = np.array(vv, dtype=np.float64)
+        a["link_mass"] = np.array([l.mass for l in self.links], dtype=np.float64)
+        a["link_com"] = np.ascontiguousarray(np.array([l.com for l in self.links], dtype=np.float64))
         assert L == len(a["link_parent"])
 
     def to_abi(self):
@@ -106,6 +110,7 @@ class RobotModel:
         r.joint_mimic_factor, r.joint_mimic_offset = _abi.dptr(a["joint_mimic_factor"]), _abi.dptr(a["joint_mimic_offset"])
         r.var_min, r.var_max = _abi.dptr(a["var_min"]), _abi.dptr(a["var_max"])
         r.var_bounded, r.var_max_velocity = _abi.iptr(a["var_bounded"]), _abi.dptr(a["var_max_velocity"])
+        r.link_mass, r.link_com = _abi.dptr(a["link_mass"]), _abi.dptr(a["link_com"])
         r._keepalive = self
         return r
 

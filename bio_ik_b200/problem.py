@@ -55,7 +55,7 @@ class Problem:
         for goal in goals:
             rec = {"goal": goal, "tip": 0, "var": 0}
             links = []
-            for link_name in goal.link_names():
+            for link_name in (goal.describe_links(rm) if hasattr(goal, "describe_links") else goal.link_names()):
                 if link_name not in rm.link_index:
                     raise RuntimeError(f"link not found {link_name}")
                 links.append(self._addTipLink(rm.link_index[link_name]))

@@ -218,3 +218,19 @@ def planar_base_arm():
     rm = RobotModel("planar_base_arm", links)
     groups = {"all": JointModelGroup(rm, "all", ["virtual_joint", "j1", "j2", "j3"], ["ee", "camera"]), "whole_arm": JointModelGroup(rm, "whole_arm", ["virtual_joint", "j1", "j2", "j3"], ["ee"])}
     return rm, groups
+
+
+def balancing_tree(seed=5):
+    """random_tree with URDF-style inertials on most links (mass, centre of mass in the link frame): the robot of the
+    BalanceGoal tests.  12 of its 13 links carry mass, so the problem has 12+ tip links (every link with mass becomes one)."""
+    rm0, _ = random_tree(seed, n_joints=9, branch_at=4)
+    rng = np.random.default_rng(100 + seed)
+    links = []
+    for i, l in enumerate(rm0.links):
+        mass = 0.0 if i == 3 else float(rng.uniform(0.2, 3.0))
+        links.append(Link(l.name, l.parent, l.joint_type, xyz=l.xyz, quat=l.quat, axis=l.axis, lower=l.lower, upper=l.upper, bounded=l.bounded, velocity=l.velocity,
+                          joint_name=l.joint_name, mass=mass, com=rng.uniform(-0.1, 0.1, 3)))
+    rm = RobotModel(f"balancing_tree{seed}", links)
+    joints = [l.joint_name for l in links if l.joint_type != JOINT_FIXED]
+    groups = {"all": JointModelGroup(rm, "all", joints, [links[9].name, links[-1].name])}
+    return rm, groups

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define BIOIK_ABI_VERSION 1
+#define BIOIK_ABI_VERSION 2 /* 2: BioikRobot::link_mass / link_com, BIOIK_GOAL_BALANCE, bioik_begin / bioik_step / bioik_get_solution */
 
 /* ---- status codes (reference: ERROR(...) -> std::runtime_error, src/utils.h:122-129) */
 enum {
@@ -65,8 +65,11 @@ enum {
     BIOIK_GOAL_JOINT_VARIABLE = 13,      /* goal_types.h:494-498 var=robot variable, p[0]=position      */
     BIOIK_GOAL_SIDE = 14,                /* goal_types.h:606-613 p[0..2]=axis p[3..5]=direction         */
     BIOIK_GOAL_DIRECTION = 15,           /* goal_types.h:637-643 p[0..2]=axis p[3..5]=direction         */
-    BIOIK_GOAL_CONE = 16                 /* goal_types.h:700-711 p[0..2]=position p[3]=position_weight
+    BIOIK_GOAL_CONE = 16,                /* goal_types.h:700-711 p[0..2]=position p[3]=position_weight
                                                                  p[4..6]=axis p[7..9]=direction p[10]=angle */
+    BIOIK_GOAL_BALANCE = 17              /* goal_types.h:540-568, src/goal_types.cpp:231-272  p[0..2]=target p[3..5]=axis.
+                                            Centre of mass over every link with BioikRobot::link_mass > 0; those links must
+                                            be tip links of the problem, in link order (what BalanceGoal::describe adds). */
 };
 
 #define BIOIK_GOAL_NPARAM 12
@@ -91,6 +94,9 @@ typedef struct BioikRobot {
     const double* var_max;           /* [n_vars] VariableBounds::max_position_                      */
     const int32_t* var_bounded;      /* [n_vars] VariableBounds::position_bounded_                  */
     const double* var_max_velocity;  /* [n_vars] VariableBounds::max_velocity_                      */
+    /* URDF inertials, read only by BalanceGoal (src/goal_types.cpp:236-250); NULL = no link has mass */
+    const double* link_mass;         /* [n_links] urdf::Link::inertial->mass (0 = none)             */
+    const double* link_com;          /* [n_links][3] urdf::Link::inertial->origin.position          */
 } BioikRobot;
 
 /* Flattened GoalInfo (src/problem.h:121-130; field set of the older struct at

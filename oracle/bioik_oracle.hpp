@@ -413,6 +413,8 @@ struct RobotModel
     std::vector<double> var_min, var_max, var_max_velocity;
     std::vector<int> var_bounded;
     std::vector<int> var_joint; // getJointOfVariable -> child link index of the joint
+    std::vector<double> link_mass; // URDF inertial mass per link (empty: none), link_com [3 * links]: inertial origin (BalanceGoal)
+    std::vector<double> link_com;
 
     static int variableCount(int joint_type)
     {
@@ -896,9 +898,18 @@ enum GoalKind
     G_JOINT_VARIABLE = 13,
     G_SIDE = 14,
     G_DIRECTION = 15,
-    G_CONE = 16
+    G_CONE = 16,
+    G_BALANCE = 17
 };
 static const int GOAL_NPARAM = 12;
+
+// BalanceGoal::balance_infos, src/goal_types.cpp:231-259
+struct BalanceInfo
+{
+    size_t tip_index; // goal_link_indices_[i]
+    Vec3 center;
+    double weight;
+};
 
 struct GoalInfo
 {
@@ -919,7 +930,27 @@ struct Problem
     std::vector<GoalInfo> goals, secondary_goals;
     std::vector<double> initial_guess;
     std::vector<double> minimal_displacement_factors;
+    std::vector<BalanceInfo> balance_infos; // filled by describeBalance() when the problem has a BalanceGoal
     double dpos = DBL_MAX, drot = DBL_MAX, dtwist = 1e-5;
+
+    // BalanceGoal::describe, src/goal_types.cpp:231-259: the links with a positive inertial mass in link order, weight = mass / total
+    void describeBalance()
+    {
+        balance_infos.clear();
+        double total = 0.0;
+        for(size_t l = 0; l < robot_model->links.size() && !robot_model->link_mass.empty(); l++)
+        {
+            double mass = robot_model->link_mass[l];
+            if(!(mass > 0)) continue;
+            size_t tip = tip_link_indices.size();
+            for(size_t t = 0; t < tip_link_indices.size(); t++)
+                if(tip_link_indices[t] == l) tip = t;
+            if(tip == tip_link_indices.size()) throw std::runtime_error("oracle: BalanceGoal needs every link with mass among the tip links");
+            balance_infos.push_back(BalanceInfo{tip, Vec3(robot_model->link_com[3 * l], robot_model->link_com[3 * l + 1], robot_model->link_com[3 * l + 2]), mass});
+            total += mass;
+        }
+        for(auto& b : balance_infos) b.weight /= total;
+    }
 
     // src/problem.cpp:206-225
     void initVelocityWeights()
@@ -1079,6 +1110,23 @@ struct Problem
             double w = p[3];
             sum += w * w * length2(Vec3(p[0], p[1], p[2]) - fb.pos);
             return sum;
+        }
+        case G_BALANCE: // src/goal_types.cpp:261-272
+        {
+            Vec3 center(0, 0, 0);
+            for(size_t i = 0; i < balance_infos.size(); i++)
+            {
+                auto& info = balance_infos[i];
+                auto& frame = tip_frames[info.tip_index];
+                Vec3 c = info.center;
+                quat_mul_vec(frame.rot, c, c);
+                c = c + frame.pos;
+                center = center + c * info.weight;
+            }
+            Vec3 target(p[0], p[1], p[2]), axis(p[3], p[4], p[5]);
+            center = center - target;
+            center = center - axis * dot(axis, center);
+            return length2(center);
         }
         default: throw std::runtime_error("oracle: unsupported goal type");
         }

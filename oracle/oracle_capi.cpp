@@ -37,6 +37,12 @@ RobotModel makeRobot(const BioikRobot* r)
     m.var_max.assign(r->var_max, r->var_max + r->n_vars);
     m.var_bounded.assign(r->var_bounded, r->var_bounded + r->n_vars);
     m.var_max_velocity.assign(r->var_max_velocity, r->var_max_velocity + r->n_vars);
+    if(r->link_mass)
+    {
+        m.link_mass.assign(r->link_mass, r->link_mass + r->n_links);
+        m.link_com.assign(3 * (size_t)r->n_links, 0.0);
+        if(r->link_com) m.link_com.assign(r->link_com, r->link_com + 3 * (size_t)r->n_links);
+    }
     m.finalize();
     return m;
 }
@@ -65,6 +71,7 @@ Problem makeProblem(const RobotModel& robot, const BioikProblem* p)
                 if(p->active_vars[i] == bg.var) gi.var_index = i;
         }
         for(int k = 0; k < GOAL_NPARAM; k++) gi.p[k] = bg.p[k];
+        if(bg.type == BIOIK_GOAL_BALANCE && pr.balance_infos.empty()) pr.describeBalance();
         if(gi.secondary)
             pr.secondary_goals.push_back(gi);
         else

@@ -66,6 +66,7 @@ inline double cos(double x)
 
 #include "ik_evolution_2.cpp"
 #include "problem.cpp"
+#include "goal_types.cpp" // BalanceGoal::describe / evaluate (TouchGoal is compiled out, as with FCL >= 0.6)
 
 #include "../include/bioik_b200.h"
 
@@ -128,6 +129,17 @@ std::shared_ptr<moveit::core::RobotModel> makeRobot(const BioikRobot* r)
             joint->mimic_factor_ = r->joint_mimic_factor[l];
             joint->mimic_offset_ = r->joint_mimic_offset[l];
             m->mimic_joints_.push_back(joint);
+        }
+        {
+            // URDF inertial of the link (read by BalanceGoal::describe only)
+            auto ul = std::make_shared<urdf::Link>();
+            if(r->link_mass && r->link_mass[l] != 0.0)
+            {
+                ul->inertial = std::make_shared<urdf::Inertial>();
+                ul->inertial->mass = r->link_mass[l];
+                if(r->link_com) ul->inertial->origin.position.x = r->link_com[3 * l], ul->inertial->origin.position.y = r->link_com[3 * l + 1], ul->inertial->origin.position.z = r->link_com[3 * l + 2];
+            }
+            m->urdf_->links_.emplace_back(link->name_, ul);
         }
         m->link_ptrs_.push_back(link);
         m->joint_ptrs_.push_back(joint);
@@ -193,6 +205,14 @@ void makeGoals(const moveit::core::RobotModel& robot, const BioikProblem* pr, co
             goal.reset(new RegularizationGoal(bg.weight)), link_goal = false;
             break;
         case BIOIK_GOAL_JOINT_VARIABLE: goal.reset(new JointVariableGoal(robot.variable_names_[bg.var], p[0], bg.weight, bg.secondary != 0)), link_goal = false; break;
+        case BIOIK_GOAL_BALANCE:
+        {
+            if(bg.secondary) throw std::runtime_error("ref harness: BalanceGoal has no secondary form");
+            auto* x = new BalanceGoal(V(p), bg.weight);
+            x->setAxis(V(p + 3));
+            goal.reset(x), link_goal = false;
+            break;
+        }
         default: throw std::runtime_error("ref harness: goal type not mapped");
         }
         if(link_goal && bg.secondary) throw std::runtime_error("ref harness: link goals have no public way to become secondary");
@@ -228,6 +248,7 @@ ProtoCache& protoCache(const BioikRobot* r, const BioikProblem* problem, const c
     appendBytes(key, r->link_origin, 7 * (size_t)r->n_links), appendBytes(key, r->joint_axis, 3 * (size_t)r->n_links);
     appendBytes(key, r->joint_mimic, r->n_links), appendBytes(key, r->joint_mimic_factor, r->joint_mimic ? r->n_links : 0), appendBytes(key, r->joint_mimic_offset, r->joint_mimic ? r->n_links : 0);
     appendBytes(key, r->var_min, r->n_vars), appendBytes(key, r->var_max, r->n_vars), appendBytes(key, r->var_bounded, r->n_vars), appendBytes(key, r->var_max_velocity, r->n_vars);
+    appendBytes(key, r->link_mass, r->link_mass ? r->n_links : 0), appendBytes(key, r->link_com, r->link_com ? 3 * (size_t)r->n_links : 0);
     appendBytes(key, problem->active_vars, problem->n_active);
     appendBytes(key, &problem->dpos, 1), appendBytes(key, &problem->drot, 1), appendBytes(key, &problem->dtwist, 1);
     if(g_proto.proto && g_proto.key == key) return g_proto;
@@ -529,6 +550,7 @@ int ref_effective_goal_params(const BioikRobot* robot, const BioikProblem* probl
                 if(auto* x = dynamic_cast<const DirectionGoal*>(goal)) W3(o, x->getAxis()), W3(o + 3, x->getDirection());
                 if(auto* x = dynamic_cast<const ConeGoal*>(goal)) W3(o, x->getPosition()), o[3] = x->getPositionWeight(), W3(o + 4, x->getAxis()), W3(o + 7, x->getDirection()), o[10] = x->getAngle();
                 if(auto* x = dynamic_cast<const JointVariableGoal*>(goal)) o[0] = x->getVariablePosition();
+                if(auto* x = dynamic_cast<const BalanceGoal*>(goal)) W3(o, x->getTarget()), W3(o + 3, x->getAxis());
             }
         }
         return 0;

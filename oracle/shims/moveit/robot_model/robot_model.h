@@ -6,6 +6,37 @@
 #include <memory>
 #include <string>
 #include <vector>
+// urdf::ModelInterface::getLink(name)->inertial: what BalanceGoal::describe reads (src/goal_types.cpp:236-250)
+namespace urdf
+{
+struct Vector3
+{
+    double x = 0, y = 0, z = 0;
+};
+struct Pose
+{
+    Vector3 position;
+};
+struct Inertial
+{
+    Pose origin;
+    double mass = 0;
+};
+struct Link
+{
+    std::shared_ptr<Inertial> inertial;
+};
+struct ModelInterface
+{
+    std::vector<std::pair<std::string, std::shared_ptr<Link>>> links_;
+    std::shared_ptr<const Link> getLink(const std::string& name) const
+    {
+        for(auto& l : links_)
+            if(l.first == name) return l.second;
+        return nullptr;
+    }
+};
+}
 namespace moveit
 {
 namespace core
@@ -108,6 +139,8 @@ public:
     std::vector<VariableBounds> bounds_;
     std::vector<const JointModel*> joint_of_variable_;
     std::vector<std::unique_ptr<JointModelGroup>> groups_;
+    std::shared_ptr<urdf::ModelInterface> urdf_ = std::make_shared<urdf::ModelInterface>();
+    const std::shared_ptr<urdf::ModelInterface>& getURDF() const { return urdf_; }
 
     const std::vector<const LinkModel*>& getLinkModels() const { return link_ptrs_; }
     size_t getLinkModelCount() const { return link_ptrs_.size(); }

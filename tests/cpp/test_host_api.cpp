@@ -87,6 +87,47 @@ int main(int argc, char** argv)
         threw = true;
     }
     CHECK(threw); // IKFactory: class not found
+    {
+        // src/problem.cpp:103-126: a goal variable outside the joint group is an error; a fixed joint's variable stays at the seed
+        threw = false;
+        try
+        {
+            JointVariableGoal torso("torso_joint", 0.1);
+            Problem p3;
+            p3.initialize(rm, arm, {&pose, &torso});
+        }
+        catch(std::runtime_error&)
+        {
+            threw = true;
+        }
+        CHECK(threw);
+        Problem p4;
+        p4.initialize(rm, arm, {&pose}, {"froll_joint"});
+        CHECK(p4.active_variables.size() == 6);
+        for(int v : p4.active_variables) CHECK(rm.variable_names[v] != "froll_joint");
+    }
+    {
+        // floating base: 7 variables with MoveIt's names, all of them active; links with mass become tips of a BalanceGoal
+        RobotModel fb;
+        RobotModel::Link w, b, l1, l2;
+        w.name = "world", w.joint_name = "world_joint";
+        b.name = "base", b.parent = "world", b.joint_name = "virtual_joint", b.joint_type = BIOIK_JOINT_FLOATING, b.mass = 5.0, b.com[2] = 0.1;
+        l1.name = "l1", l1.parent = "base", l1.joint_name = "j1", l1.joint_type = BIOIK_JOINT_REVOLUTE, l1.origin[2] = 0.25, l1.lower = -2.5, l1.upper = 2.5, l1.mass = 1.0, l1.com[0] = 0.1;
+        l2.name = "l2", l2.parent = "l1", l2.joint_name = "j2", l2.joint_type = BIOIK_JOINT_REVOLUTE, l2.origin[0] = 0.3, l2.axis[0] = 0, l2.axis[1] = 1, l2.axis[2] = 0, l2.lower = -1.8, l2.upper = 1.8;
+        fb.addLink(w), fb.addLink(b), fb.addLink(l1), fb.addLink(l2);
+        fb.finalize();
+        CHECK(fb.getVariableCount() == 9 && fb.variable_names[3] == "virtual_joint/rot_x" && fb.var_bounded[3] == 1 && fb.var_bounded[0] == 0);
+        JointModelGroup all{"all", {"virtual_joint", "j1", "j2"}, {"l2"}};
+        PositionGoal tip("l2", Vector3(0.3, 0, 0.5));
+        BalanceGoal bal(Vector3(0, 0, 0), 0.5);
+        Problem pb;
+        pb.initialize(fb, all, {&tip, &bal});
+        CHECK(pb.active_variables.size() == 9);
+        CHECK(pb.tip_link_indices.size() == 3 && pb.tip_link_indices[0] == 3 && pb.tip_link_indices[1] == 1 && pb.tip_link_indices[2] == 2);
+        CHECK(pb.goals[1].type == BIOIK_GOAL_BALANCE && pb.goals[1].tip == 1 && pb.goals[1].p[5] == 1.0);
+        BioikRobot abi = fb.toABI();
+        CHECK(abi.link_mass && abi.link_mass[1] == 5.0 && abi.link_com[3 * 1 + 2] == 0.1);
+    }
 
     if(!gpu)
     {
@@ -157,6 +198,12 @@ int main(int argc, char** argv)
         }
         std::printf("host api ok (islands): %d / %d solved\n", iok, Q);
         CHECK(iok >= Q - 1);
+        // the same through the resumable interface: begin, step() one at a time, getSolution - the same bits
+        solver.begin(qgp, qseeds, islands, irs, 0, 0);
+        for(int k = 0; k < 6; k++) solver.step(1);
+        auto one = solver.getSolution(false);
+        auto whole = solver.solveIslands(qgp, qseeds, islands, irs, 6, 0, false);
+        CHECK(one.solutions == whole.solutions && one.island == whole.island);
     }
     return 0;
 }

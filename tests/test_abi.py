@@ -25,11 +25,11 @@ def test_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     lib.bioik_abi_version.restype = C.c_int
-    assert lib.bioik_abi_version() == 1
+    assert lib.bioik_abi_version() == 2
     # POD layout agreed with the header (LP64)
     assert C.sizeof(_abi.BioikGoal) == 16 + 8 + 8 * _abi.GOAL_NPARAM
     assert C.sizeof(_abi.BioikSolverCfg) == 24
-    assert C.sizeof(_abi.BioikRobot) == 8 + 12 * 8
+    assert C.sizeof(_abi.BioikRobot) == 8 + 14 * 8
     assert C.sizeof(_abi.BioikProblem) == 3 * 16 + 3 * 8
 
 

@@ -171,3 +171,29 @@ def test_resumable_steps_cost_no_restart(oracle):
         assert np.array_equal(one[key], many[key]) and np.array_equal(one[key], whole[key]), key
     assert np.all(one["steps"] == k)
     assert l1 - l0 <= (l2 - l1) + 4 * k  # O(k) launches either way (queue set-up, solve kernel and the active-run count per call)
+
+
+@pytest.mark.gpu
+def test_adapter_flattens_a_balance_goal_from_the_urdf_inertials(oracle, monkeypatch):
+    """BalanceGoal through the reference's types: the adapter reads the link inertials from RobotModel::getURDF() like
+    BalanceGoal::describe does, the reference's Problem::initialize makes every link with mass a tip link, and the device answer equals
+    the C ABI called with the same flattened problem."""
+    from bio_ik_b200.solver import IKSolver
+    lib = load_adapter()
+    ref = oracle_lib.Reference("strict")
+    islands, steps, random_seed = 8, 5, 2
+    monkeypatch.setenv("BIOIK_B200_ISLANDS", str(islands))
+    rm, groups = robots.balancing_tree()
+    g = groups["all"]
+    pr = Problem().initialize(rm, g, [G.PoseGoal(g.tip_links[0]), G.BalanceGoal((0.05, -0.02, 0.3), 0.8, axis=(0.1, 0.2, 0.97))])
+    rng = np.random.default_rng(4)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 1, rng)
+    gp = pr.default_goal_params()[None]
+    r, p = rm.to_abi(), pr.to_abi()
+    got = np.zeros((1, rm.n_vars))
+    rc = lib.adapter_steps(C.byref(r), C.byref(p), b"bio2_memetic_b200", random_seed, 1, _abi.dptr(np.ascontiguousarray(gp)), _abi.dptr(np.ascontiguousarray(seeds)), steps, 0, _abi.dptr(got))
+    assert rc == 0, lib.ref_last_error().decode()
+    direct = IKSolver(ref.effective_robot(rm), mode="bio2_memetic", population=18, random_seed=random_seed, device=0).initialize(pr)
+    rs = (random_seed + np.arange(islands)).astype(np.uint32)
+    want = direct.solve_islands(ref.effective_goal_params(rm, pr, gp, 1), seeds, islands, steps, rng_seeds=rs, early_exit=2, wrap=False)
+    assert np.array_equal(got[0], want["solutions"][0]) and not np.array_equal(got[0], seeds[0])

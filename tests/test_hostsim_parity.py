@@ -223,3 +223,26 @@ def test_persistent_kernel_is_bit_identical_to_the_oracle(sim, oracle, B, pop, m
     b = sim.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, steps, early_exit=early, fast=10)
     for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps") if not early else ("solutions", "fitness", "success", "steps"):
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("first", [False, True])
+def test_balance_goal_on_the_device_code(sim, oracle, first):
+    """BalanceGoal (every link with mass a tip link: 12 tips here) through the kernel source: generic generation kernel and the
+    fused serial kernel, goal first or in the middle of the goal list."""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.balancing_tree()
+    g = groups["all"]
+    bal = G.BalanceGoal((0.05, -0.02, 0.3), 0.8, axis=(0.1, 0.2, 0.97))
+    gl = ([bal] if first else []) + [G.PoseGoal(g.tip_links[0])] + ([] if first else [bal]) + [G.PositionGoal(g.tip_links[1], weight=0.5)]
+    pr = Problem().initialize(rm, g, gl)
+    rng = np.random.default_rng(2)
+    B = 3
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    cfg = oracle_lib.make_cfg(population=20)
+    a = oracle.solve(rm, pr, cfg, gp, seeds, 1 + np.arange(B), 4)
+    for fast in (False, True):
+        b = sim.solve(rm, pr, cfg, gp, seeds, 1 + np.arange(B), 4, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness", "success", "steps"):
+            assert np.array_equal(a[k], b[k]), (k, fast)

@@ -275,3 +275,42 @@ def test_random_trees(ref, oracle):
             gp[:, gi, 0:7] = tips[:, rec["tip"], 0:7]
         cfg = oracle_lib.make_cfg(population=18)
         compare(oracle, ref, rm, pr, cfg, gp, seeds, 5 + np.arange(B, dtype=np.uint32), 5)
+
+
+def balance_problem(first=False):
+    rm, groups = robots.balancing_tree()
+    g = groups["all"]
+    bal = G.BalanceGoal((0.05, -0.02, 0.3), 0.8, axis=(0.1, 0.2, 0.97))
+    gl = ([bal] if first else []) + [G.PoseGoal(g.tip_links[0])] + ([] if first else [bal]) + [G.PositionGoal(g.tip_links[1], weight=0.5)]
+    return rm, Problem().initialize(rm, g, gl)
+
+
+def test_balance_goal_against_the_references_own_class(ref, oracle):
+    """BalanceGoal (goal_types.h:540-568, src/goal_types.cpp:231-272, compiled in place through a urdf::ModelInterface shim that
+    carries the link inertials): every link with mass becomes a tip link (12 here), the centre of mass is accumulated in link
+    order.  Approximate fitness and whole solver trajectories are bit-identical to the reference's class.
+    The reference can only take a BalanceGoal that is NOT the first goal of a query: BalanceGoal::describe reads
+    GoalContext::getRobotModel() (goal_types.cpp:236) before Problem::initialize has set joint_model_group_ (problem.cpp:136 vs
+    :180) - an uninitialised pointer that happens to hold the previous goal's value from the second goal on.  Oracle and device
+    take it in any position (checked against each other below)."""
+    rm, pr = balance_problem()
+    assert len(pr.tip_link_indices) == 12 and pr.tip_link_indices[0] == 9  # the PoseGoal's tip first, then the links with mass in link order
+    rng = np.random.default_rng(1)
+    B, M, n = 12, 6, len(pr.active_variables)
+    base = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng)
+    genes = base[:, pr.active_variables][:, None, :] + rng.normal(0, 0.2, (B, M, n))
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    b = ref.approx_fitness(rm, pr, gp, seeds, base, genes)
+    oracle.component_flags(LIBM)
+    try:
+        prim, _ = oracle.approx_fitness(ref.effective_robot(rm), pr, ref.effective_goal_params(rm, pr, gp, B), seeds, base, genes)
+    finally:
+        oracle.component_flags(0)
+    assert np.array_equal(prim, b["primary"]) and np.abs(prim).min() > 0
+    compare(oracle, ref, rm, pr, oracle_lib.make_cfg(population=18), gp, seeds, 1 + np.arange(B, dtype=np.uint32), 5)
+    # the goal really contributes: without it the fitness differs
+    rm2, groups2 = robots.balancing_tree()
+    pr0 = Problem().initialize(rm2, groups2["all"], [G.PoseGoal(groups2["all"].tip_links[0]), G.PositionGoal(groups2["all"].tip_links[1], weight=0.5)])
+    p0, _ = oracle.approx_fitness(rm2, pr0, np.repeat(pr0.default_goal_params()[None], B, 0), seeds, base, genes)
+    assert not np.array_equal(p0, prim)
