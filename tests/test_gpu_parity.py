@@ -531,3 +531,54 @@ def test_gpu_against_the_reference_as_shipped(oracle, name, B):
     tips = oracle.fk(w.robot, w.problem, got["solutions"], libm=True)[:, 0]
     ok = got["success"] != 0
     assert ok.sum() > 0.9 * B and np.abs(tips[ok, :3] - w.goal_params[ok, 0, :3]).max() < 1e-4
+
+
+def test_cached_graph_survives_reallocation_by_the_device_entry_point(oracle):
+    """ADVICE r01: bioik_solve_batch caches a CUDA graph that bakes in the addresses of the state, schedule and staging buffers;
+    bioik_solve_batch_device with a larger batch or more steps reallocates them.  The cached graph must be dropped, not replayed on
+    freed memory: solve_batch x2 (eager, then captured), a bigger device-pointer solve, solve_batch again - same bits as before."""
+    torch = pytest.importorskip("torch")
+    w = workloads.make("cfg2", ofk(oracle), batch=96)
+    solver = gpu_util.make_solver(w, 32)
+    first = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 5)
+    second = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 5)  # captures the graph
+    third = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 5)   # replays it
+    for k in ("solutions", "fitness", "success"):
+        assert np.array_equal(first[k], second[k]) and np.array_equal(first[k], third[k])
+    big = workloads.make("cfg2", ofk(oracle), batch=700)
+    dev = torch.device("cuda:0")
+    gp, seeds = torch.from_numpy(big.goal_params).to(dev), torch.from_numpy(big.seeds).to(dev)
+    rs = torch.from_numpy(big.rng_seeds.astype(np.int64)).to(dev).to(torch.int32)
+    sol = torch.empty((700, big.robot.n_vars), dtype=torch.float64, device=dev)
+    fit, succ, stp = torch.empty(700, dtype=torch.float64, device=dev), torch.empty(700, dtype=torch.int32, device=dev), torch.empty(700, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    solver.solve_batch_device(700, gp.data_ptr(), seeds.data_ptr(), rs.data_ptr(), 40, False, sol.data_ptr(), fit.data_ptr(), succ.data_ptr(), stp.data_ptr(), stream=st.cuda_stream)  # larger B and more steps
+    st.synchronize()
+    solver.synchronize()  # torch's default stream is handle 0 = "use the context's own stream" for the ABI
+    want = oracle.solve(big.robot, big.problem, oracle_lib.make_cfg(population=32), big.goal_params, big.seeds, big.rng_seeds, 40)
+    assert np.array_equal(sol.cpu().numpy(), want["solutions"])
+    again = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 5)
+    for k in ("solutions", "fitness", "success"):
+        assert np.array_equal(first[k], again[k]), k
+
+
+def test_cancel_does_not_stick_to_the_next_device_solve(oracle):
+    """ADVICE r01: bioik_cancel sets the device flag every kernel reads; like IKParallel::solve (src/ik_parallel.h:211-212) every
+    solve entry point - the device-pointer one included - clears it when it starts, so a cancel that lands after a solve has finished
+    does not turn the next solve into a no-op."""
+    torch = pytest.importorskip("torch")
+    w = workloads.make("cfg2", ofk(oracle), batch=64)
+    solver = gpu_util.make_solver(w, 32)
+    want = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 6)
+    solver.cancel()
+    torch.cuda.synchronize()  # the cancel's copy (its own stream) has landed: the flag is set on the device
+    dev = torch.device("cuda:0")
+    gp, seeds = torch.from_numpy(w.goal_params).to(dev), torch.from_numpy(w.seeds).to(dev)
+    rs = torch.from_numpy(w.rng_seeds.astype(np.int64)).to(dev).to(torch.int32)
+    sol = torch.empty((64, w.robot.n_vars), dtype=torch.float64, device=dev)
+    fit, succ, stp = torch.empty(64, dtype=torch.float64, device=dev), torch.empty(64, dtype=torch.int32, device=dev), torch.empty(64, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    solver.solve_batch_device(64, gp.data_ptr(), seeds.data_ptr(), rs.data_ptr(), 6, False, sol.data_ptr(), fit.data_ptr(), succ.data_ptr(), stp.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    solver.synchronize()  # torch's default stream is handle 0 = "use the context's own stream" for the ABI
+    assert np.array_equal(sol.cpu().numpy(), want["solutions"]) and int(stp.min().item()) == 6
