@@ -414,7 +414,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     const int warps_per_block = BIOIK_EVOLVE_WPB;
     if(R.fast)
     {
-        FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1};
+        FastSmem L = fast_smem_layout(P);
         R.evolve_smem = (size_t)warps_per_block * (32 / R.evolve_lpt) * L.total() * sizeof(double);
         if(R.evolve_smem > 48 * 1024) CU(ctx, cudaFuncSetAttribute((const void*)R.fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.evolve_smem));
     }

@@ -69,10 +69,11 @@ struct FastSmem
 {
     int n, T, G, nj;
     int lean = 0; // 1: no per-child fitness arrays (only the pre-selection of problems with secondary goals reads them)
+    int pairs = 0; // tip-major form: the delta frames of the (tip, gene) pairs of DProblem::tip_gene only, in list order (0: dense [T][n])
     __host__ __device__ int off_rec() const { return 0; }                        // [n][4]  g0, base, clip_min, clip_max
     __host__ __device__ int off_term() const { return off_rec() + 4 * n; }       // [n][6]  pg[parity] * gradient_factor
-    __host__ __device__ int off_delta() const { return off_term() + 6 * n; }     // [T][n][8]
-    __host__ __device__ int off_par() const { return off_delta() + 8 * T * n; }  // [2 buffers][g0,g1,gr0,gr1][n]
+    __host__ __device__ int off_delta() const { return off_term() + 6 * n; }     // [T][n][8], or [pairs][8]
+    __host__ __device__ int off_par() const { return off_delta() + 8 * (pairs ? pairs : T * n); }  // [2 buffers][g0,g1,gr0,gr1][n]
     __host__ __device__ int off_pg() const { return off_par() + 8 * n; }         // [2][n] mix(gr0, gr1, fmix)
     __host__ __device__ int off_tip0() const { return off_pg() + 2 * n; }        // [T][8]
     __host__ __device__ int off_gp() const { return off_tip0() + 8 * T; }        // [G][12]
@@ -80,9 +81,16 @@ struct FastSmem
     __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
     __host__ __device__ int off_fit() const { return off_jq() + (nj ? 4 * FAST_MAX_JOINT_GOALS * n : 0); } // [256] primary fitness per child slot
     __host__ __device__ int off_sf() const { return off_fit() + (lean ? 0 : 256); }   // [256] secondary fitness per child slot
-    __host__ __device__ int off_gv() const { return off_sf() + (lean ? 0 : 256); }                 // [G][4 children][32 lanes] link-goal values of the tip-major form (T > 1)
-    __host__ __device__ int total() const { return ((off_gv() + (T > 1 ? G * 128 : 0)) + 1) & ~1; }
+    __host__ __device__ int total() const { return ((off_sf() + (lean ? 0 : 256)) + 1) & ~1; }
 };
+
+// problems with three or more tips run the tip-major form of the generation kernel (select_evolve_fast)
+__host__ __device__ inline bool fast_tip_major(const DProblem& P) { return P.T > 2; }
+// the shared-memory plan of one task of the generation kernel select_evolve_fast picks for P
+__host__ __device__ inline FastSmem fast_smem_layout(const DProblem& P)
+{
+    return FastSmem{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1, fast_tip_major(P) ? P.tip_gene_start[P.T] : 0};
+}
 
 template <int T> BIOIK_HD void select_frame(const double (&F)[T][7], int tip, double* f)
 {
@@ -280,32 +288,15 @@ __device__ __forceinline__ double fast_eval_one(const DProblem& P, int n, const 
     return prim;
 }
 
-// the same for any number of tips, tip by tip (only one tip's frame is live at a time); used by the tip-major kernel form
+// the same for any number of tips, goal by goal: a link goal runs the FMA chain of its tip over that tip's gene list (kept
+// while consecutive goals read the same tip), so only one tip's frame is live at a time; used by the tip-major kernel form
+// (s_delta then holds the delta frames of the (tip, gene) pairs of DProblem::tip_gene, in list order)
 template <bool JOINT> __device__ __forceinline__ double fast_eval_one_tips(const DProblem& P, int n, const double* x, const double* s_rec, const double* s_delta, const double* s_tip0, const double* s_gp, const double* s_jrec,
                                                                            const double* seed)
 {
-    double gval[MAX_GOALS];
-    for(int t = 0; t < P.T; t++)
-    {
-        double F[7];
-#pragma unroll
-        for(int j = 0; j < 7; j++) F[j] = s_tip0[8 * t + j];
-        for(int idx = P.tip_gene_start[t]; idx < P.tip_gene_start[t + 1]; idx++)
-        {
-            const int i = P.tip_gene[idx];
-            const double d = x[i] - s_rec[4 * i + 1];
-            const double* D = s_delta + ((size_t)t * n + i) * 8;
-#pragma unroll
-            for(int j = 0; j < 7; j++) F[j] = BIOIK_FMA(d, D[j], F[j]);
-        }
-        for(int g = 0; g < P.G; g++)
-        {
-            const DGoal& gl = P.goals[g];
-            if(gl.secondary || gl.tip != t || (JOINT && is_joint_goal(gl.type))) continue;
-            gval[g] = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F);
-        }
-    }
     double prim = 0.0;
+    double F[7];
+    int tip_live = -1;
     for(int g = 0; g < P.G; g++)
     {
         const DGoal& gl = P.goals[g];
@@ -324,7 +315,24 @@ template <bool JOINT> __device__ __forceinline__ double fast_eval_one_tips(const
                     joint_goal_accumulate(gl.type, gl.var_index, i, x[i], s_rec[4 * i + 3], s_jrec[4 * i + 0], s_jrec[4 * i + 1], s_jrec[4 * i + 2], s_jrec[4 * i + 3], s_gp[g * GOAL_NPARAM], v);
         }
         else
-            v = gval[g];
+        {
+            const int t = gl.tip;
+            if(t != tip_live)
+            {
+#pragma unroll
+                for(int j = 0; j < 7; j++) F[j] = s_tip0[8 * t + j];
+                for(int idx = P.tip_gene_start[t]; idx < P.tip_gene_start[t + 1]; idx++)
+                {
+                    const int i = P.tip_gene[idx];
+                    const double d = x[i] - s_rec[4 * i + 1];
+                    const double* D = s_delta + (size_t)idx * 8;
+#pragma unroll
+                    for(int j = 0; j < 7; j++) F[j] = BIOIK_FMA(d, D[j], F[j]);
+                }
+                tip_live = t;
+            }
+            v = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F);
+        }
         prim += v * gl.weight_sq;
     }
     return prim;
@@ -370,18 +378,30 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 nj++;
             }
 
-    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1};
+    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
     const int TT = TM ? P.T : T; // tips of the problem
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
-    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf(), *s_gv = W + L.off_gv();
+    double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
 
     // ---- stage the task -------------------------------------------------------------------
-    for(int k = lane; k < TT * n * 7; k += LPT)
+    if(TM)
     {
-        int ti = k / 7, c7 = k - ti * 7;
-        s_delta[ti * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + k];
+        // only the (tip, gene) pairs with a delta frame that can be non-zero, in the order the chains read them
+        for(int k = lane; k < L.pairs * 7; k += LPT)
+        {
+            const int idx = k / 7, c7 = k - idx * 7;
+            int t = 0;
+            while(P.tip_gene_start[t + 1] <= idx) t++;
+            s_delta[idx * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + ((size_t)t * n + P.tip_gene[idx]) * 7 + c7];
+        }
     }
+    else
+        for(int k = lane; k < TT * n * 7; k += LPT)
+        {
+            int ti = k / 7, c7 = k - ti * 7;
+            s_delta[ti * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + k];
+        }
     for(int k = lane; k < TT * 7; k += LPT) s_tip0[(k / 7) * 8 + (k % 7)] = S.tip0[(size_t)task * TT * 7 + k];
     for(int i = lane; i < n; i += LPT)
     {
@@ -510,11 +530,13 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
 #pragma unroll
                     for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++) acc[k][j] = 0.0;
             }
+            double tm_prim[TM ? CH : 1], tm_sec[TM ? CH : 1];
             if(TM)
             {
-                // ---- tip-major form: for every tip, the FMA chain over the genes that can move it (ascending = the order of the
-                // gene-major chain restricted to that tip; the skipped genes have an all-zero delta frame, fma(d, 0, F) == F), then
-                // the link goals of that tip.  Only 7 accumulators per child are live, whatever the number of tips.
+                // ---- tip-major form: a tip's frames are the FMA chain over the genes that can move it (ascending = the order of the
+                // gene-major chain restricted to that tip; the skipped genes have an all-zero delta frame, fma(d, 0, F) == F), run
+                // when the first goal of that tip comes up in goal order.  Only 7 accumulators per child are live, whatever the
+                // number of tips.
                 auto gene_value = [&](int i, int k) { // :293-297 for child k of this lane
                     double gene = s_rec[4 * i + 0];
                     gene += BIOIK_LDG(mt + (size_t)i * R + jbase + LPT * k); // gene += r * f
@@ -546,35 +568,93 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                                 }
                             }
                     }
-                for(int t = 0; t < TT; t++)
+                // weighted sums in goal order (src/problem.cpp:251-257): a link goal finds its tip's frames in F (kept while
+                // consecutive goals read the same tip), a joint-space goal its accumulator
+                int tip_live = -1, jn = 0;
+#pragma unroll
+                for(int k = 0; k < CH; k++) tm_prim[k] = 0.0, tm_sec[k] = 0.0;
+                for(int g = 0; g < G; g++)
                 {
-#pragma unroll
-                    for(int k = 0; k < CH; k++)
-#pragma unroll
-                        for(int j = 0; j < 7; j++) F[k][0][j] = s_tip0[8 * t + j];
-                    const int i1 = P.tip_gene_start[t + 1];
-                    for(int idx = P.tip_gene_start[t]; idx < i1; idx++)
+                    const DGoal& gl = P.goals[g];
+                    double v[CH];
+                    if(JOINT && is_joint_goal(gl.type))
                     {
-                        const int i = P.tip_gene[idx];
-                        const double base = s_rec[4 * i + 1];
-                        const double* D = s_delta + ((size_t)t * n + i) * 8;
-                        double Dv[7];
-#pragma unroll
-                        for(int j = 0; j < 7; j++) Dv[j] = D[j];
 #pragma unroll
                         for(int k = 0; k < CH; k++)
                         {
-                            const double d = gene_value(i, k) - base; // :1086
+                            v[k] = 0.0;
 #pragma unroll
-                            for(int j = 0; j < 7; j++) F[k][0][j] = BIOIK_FMA(d, Dv[j], F[k][0][j]);
+                            for(int j = 0; j < FAST_MAX_JOINT_GOALS; j++)
+                                if(j == jn) v[k] = acc[k][j];
+                            if(gl.type == G_JOINT_VARIABLE && gl.var_index < 0)
+                            {
+                                double dd = s_gp[g * GOAL_NPARAM] - seed[-1 - gl.var_index];
+                                v[k] = dd * dd;
+                            }
                         }
+                        jn++;
                     }
-                    for(int g = 0; g < G; g++)
+                    else if(gl.secondary)
                     {
-                        const DGoal& gl = P.goals[g];
-                        if(gl.secondary || gl.tip != t || is_joint_goal(gl.type)) continue;
+                        // secondary goals see null_tip_frames (identity), src/ik_base.h:163
+                        const double f[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0};
+                        const double vv = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, f);
 #pragma unroll
-                        for(int k = 0; k < CH; k++) s_gv[((size_t)g * 4 + k) * 32 + lane] = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F[k][0]);
+                        for(int k = 0; k < CH; k++) v[k] = vv;
+                    }
+                    else
+                    {
+                        const int t = gl.tip;
+                        if(t != tip_live)
+                        {
+                            tip_live = t;
+#pragma unroll
+                            for(int k = 0; k < CH; k++)
+#pragma unroll
+                                for(int j = 0; j < 7; j++) F[k][0][j] = s_tip0[8 * t + j];
+                            int idx = P.tip_gene_start[t];
+                            const int i1 = P.tip_gene_start[t + 1];
+                            // mutation terms are fetched one list entry ahead of their use
+                            double m[CH];
+                            int i = idx < i1 ? P.tip_gene[idx] : 0;
+#pragma unroll
+                            for(int k = 0; k < CH; k++) m[k] = BIOIK_LDG(mt + (size_t)i * R + jbase + LPT * k);
+                            for(; idx < i1; idx++)
+                            {
+                                const int inext = idx + 1 < i1 ? P.tip_gene[idx + 1] : i;
+                                double mnext[CH];
+#pragma unroll
+                                for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mt + (size_t)inext * R + jbase + LPT * k);
+                                const double g0 = s_rec[4 * i + 0], base = s_rec[4 * i + 1], lo = s_rec[4 * i + 2], hi = s_rec[4 * i + 3];
+                                const double* D = s_delta + (size_t)idx * 8;
+                                double Dv[7];
+#pragma unroll
+                                for(int j = 0; j < 7; j++) Dv[j] = D[j];
+#pragma unroll
+                                for(int k = 0; k < CH; k++)
+                                {
+                                    double gene = g0;
+                                    gene += m[k];          // gene += r * f      (:293)
+                                    gene += tp[k][6 * i];  // gene += gradient   (:296)
+                                    gene = clampd(gene, lo, hi);
+                                    const double d = gene - base; // :1086
+#pragma unroll
+                                    for(int j = 0; j < 7; j++) F[k][0][j] = BIOIK_FMA(d, Dv[j], F[k][0][j]);
+                                    m[k] = mnext[k];
+                                }
+                                i = inext;
+                            }
+                        }
+#pragma unroll
+                        for(int k = 0; k < CH; k++) v[k] = link_goal_value(gl.type, s_gp + g * GOAL_NPARAM, F[k][0]);
+                    }
+#pragma unroll
+                    for(int k = 0; k < CH; k++)
+                    {
+                        if(gl.secondary)
+                            tm_sec[k] += v[k] * gl.weight_sq;
+                        else
+                            tm_prim[k] += v[k] * gl.weight_sq;
                     }
                 }
             }
@@ -711,7 +791,9 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                     q1 = lt1 ? pk : q1;
                     continue;
                 }
-                if(GSPEC == 1)
+                if(TM)
+                    prim = tm_prim[k], sec = tm_sec[k];
+                else if(GSPEC == 1)
                     prim += link_goal_value(G_POSE, s_gp, F[k][0]) * wsq0;
                 else
                 {
@@ -735,9 +817,6 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                         }
                         else
                         {
-                            if(TM && !gl.secondary)
-                                v = s_gv[((size_t)g * 4 + k) * 32 + lane]; // evaluated when the tip's frame was complete
-                            else
                             {
                                 double f[7];
                                 select_frame<T>(F[k], gl.secondary ? 0 : gl.tip, f);
@@ -944,7 +1023,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
     const int warp_in_block = threadIdx.x >> 5;
     const int task = (blockIdx.x * (blockDim.x >> 5) + warp_in_block) * TPW + grp;
     const int n = NG ? NG : P.n;
-    FastSmem L{n, TM ? P.T : T, P.G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1};
+    FastSmem L{n, TM ? P.T : T, P.G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
     evolve_fast_task<T, CH, GSPEC, JOINT, NG, TM, LPT>(P, S, step, mtab, smem + (size_t)(warp_in_block * TPW + grp) * L.total(), task, lane, lane0, gmask);
 }
 
@@ -1000,7 +1079,7 @@ inline EvolveFastKernel select_evolve_fast(const DProblem& P, int C, int ch_cap 
     }
     if(single_pose) return cpl >= 3 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 4, 1, false>) : (cpl == 2 ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 2, 1, false>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, 1, 1, false>));
     if(T == 1) return cpl >= 3 ? BIOIK_PICK(1, 4) : (cpl == 2 ? BIOIK_PICK(1, 2) : BIOIK_PICK(1, 1));
-    if(T == 2) return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1); // two tips still fit the gene-major register block (cfg3: 9.9 vs 10.1 ms per pass)
+    if(!fast_tip_major(P)) return cpl >= 2 ? BIOIK_PICK(2, 2) : BIOIK_PICK(2, 1); // two tips still fit the gene-major register block (cfg3: 9.9 vs 10.1 ms per pass)
     // three or more tips: the tip-major form (one tip's accumulators at a time, so the register block does not depend on T; cfg5: 54.7 vs 57.6 ms)
 #define BIOIK_PICK_TM(CC) (J ? BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, CC, 0, true, 0, true>) : BIOIK_NAMED_AS(EvolveFastKernel, k_evolve_fast<1, CC, 0, false, 0, true>))
     return cpl >= 3 ? BIOIK_PICK_TM(4) : (cpl == 2 ? BIOIK_PICK_TM(2) : BIOIK_PICK_TM(1));

@@ -177,6 +177,31 @@ def test_mixed_goals_fast_kernel(sim, oracle):
             assert np.array_equal(a[k], b[k]), (k, fast)
 
 
+def test_mixed_goals_tip_major_kernel(sim, oracle):
+    """Five tips (the tip-major generation kernel): link goals of several kinds with a tip read again later in the goal list, a
+    secondary link goal (a setSecondary link goal sees the identity frames), primary and secondary joint-space goals."""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.shadow_like_hand()
+    g = groups["hand"]
+    t = g.tip_links
+    late = G.LineGoal(t[3], (0.0, 0.0, 0.35), (0, 1, 0), 0.4)
+    late.secondary_ = True
+    gl = [G.PositionGoal(t[0], (0.03, 0.0, 0.36)), G.OrientationGoal(t[1], (0, 0, 0, 1), 0.5), G.MaxDistanceGoal(t[0], (0.0, 0.0, 0.3), 0.05, 0.8), G.JointVariableGoal("WRJ1", 0.1, 2.0),
+          G.PoseGoal(t[2], (0.0, 0.02, 0.37), (0, 0, 0, 1), 0.7), G.CenterJointsGoal(0.5, secondary=False), late, G.MinimalDisplacementGoal(1.5), G.PlaneGoal(t[4], (0, 0, 0.33), (0, 0, 1), 0.6),
+          G.ConeGoal(t[1], (0, 0, 1), (0, 0.6, 0.8), 0.4, weight=0.3)]
+    pr = Problem().initialize(rm, g, gl)
+    rng = np.random.default_rng(9)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 3, rng)
+    rs = np.array([7, 8, 9], dtype=np.uint32)
+    cfg = oracle_lib.make_cfg(population=45)
+    a = oracle.solve(rm, pr, cfg, None, seeds, rs, 3)
+    for fast in (False, True, 6):
+        b = sim.solve(rm, pr, cfg, None, seeds, rs, 3, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(a[k], b[k]), (k, fast)
+
+
 @pytest.mark.parametrize("variant", [2, 3, 4, 5])
 def test_serial_kernel_placement_variants(sim, oracle, variant):
     """The fused serial kernel keeps delta frames / link frames in shared memory, in the HBM state or in local
