@@ -29,10 +29,19 @@ struct ProbeGenes
     BIOIK_HD double operator[](int k) const { return k == i ? v : ind[k]; }
 };
 
-// shared-memory block of one group, in doubles
+// the one tip frame a link goal of a probe reads, held in registers (goal_value offsets its frame argument by 7 * tip)
+struct ProbeFrame
+{
+    const double* f;
+    BIOIK_HD ProbeFrame operator+(int) const { return *this; }
+    BIOIK_HD double operator[](int k) const { return f[k]; }
+};
+
+// shared-memory block of one group, in doubles.  K = number of (tip, gene) pairs where the gene can move the tip
+// (DProblem::tip_gene; every other delta frame is all zero and never read)
 struct GroupLayout
 {
-    int n, T, G, W;
+    int n, T, G, W, K, stale;
     __host__ __device__ int o_ind() const { return 0; }
     __host__ __device__ int o_graw() const { return n; }
     __host__ __device__ int o_grad() const { return 2 * n; }
@@ -42,18 +51,32 @@ struct GroupLayout
     __host__ __device__ int o_clip() const { return 6 * n; } // [n][2]
     __host__ __device__ int o_tip0() const { return 8 * n; }
     __host__ __device__ int o_f2() const { return o_tip0() + 7 * T; }
-    __host__ __device__ int o_pl() const { return o_f2() + 7 * T; } // [W][7T] per-lane frames; rows 0 and 1 double as the f1 / f3 frames
-    __host__ __device__ int o_delta() const { return o_pl() + W * 7 * T; }
-    __host__ __device__ int o_gp() const { return o_delta() + 7 * T * n; }
-    __host__ __device__ int o_sc() const { return o_gp() + GOAL_NPARAM * G; }
+    __host__ __device__ int o_pl() const { return o_f2() + 7 * T; }     // [2][7T] frames of the two support points
+    __host__ __device__ int o_delta() const { return o_pl() + 14 * T; } // [K][7] delta frames in pair order (tip-major, genes ascending)
+    __host__ __device__ int o_dxa() const { return o_delta() + 7 * K; } // [K] x - base of the pair's gene: current genes / support point a / candidate
+    __host__ __device__ int o_dxb() const { return o_dxa() + K; }       // [K] the same for support point b
+    __host__ __device__ int o_gp() const { return o_dxb() + K; }
+    __host__ __device__ int o_gv() const { return o_gp() + GOAL_NPARAM * G; } // [3][G] goal values: current genes; support point a / candidate; support point b
+    __host__ __device__ int o_sc() const { return o_gv() + 3 * G; }
     __host__ __device__ int o_carry() const { return o_sc() + 8; }               // [7T] reference-quirk mode: the frames left in phenotypes3
-    __host__ __device__ int o_prev() const { return o_carry() + 7 * T; }          // [T][n] int32: last earlier gene that moves tip t (-1: none)
-    __host__ __device__ int total() const { return (o_prev() + (T * n + 1) / 2) | 1; } // odd stride: the groups of a warp start in different banks
+    __host__ __device__ int o_int() const { return o_carry() + (stale ? 7 * T : 0); }
+    // int32: pair_start [T + 1], pair_gene [K], pair_of [T][n] (-1: the gene cannot move the tip); reference-quirk mode:
+    // prev_pair [T][n] = pair of the last earlier gene that moves tip t (-1: none)
+    __host__ __device__ int ints() const { return T + 1 + K + T * n + (stale ? T * n : 0); }
+    __host__ __device__ int total() const { return (o_int() + (ints() + 1) / 2) | 1; } // odd stride: the groups of a warp start in different banks
 };
 
 inline int memetic_group_width(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : 32); }
 
 // W lanes per task, 32 / W tasks per warp; blockDim.x = 32 * warps (any number of warps, no block-level sync)
+//
+// Schedule of one iteration (values as in the thread-per-task kernel, see the header):
+//   * a full approximation = 7T FMA chains, each over the pairs of its tip only, on 7T lanes; x - base (:1086) is formed once
+//     per pair by the phase that produces x;
+//   * Goal::evaluate of every goal on its own lane, then the weighted sum in goal order on one lane (src/problem.cpp:251-257);
+//   * a probe builds the one frame each link goal reads in registers (computeApproximateMutation1 of ONE variable);
+//   * the candidate of an accepted iteration IS the next iteration's individual: its frames and goal values (f4p, and the
+//     secondary goals for fa) are kept instead of being recomputed by (1) and (2).
 //
 // STALE = the reference-quirk mode (bioik_set_option BIOIK_OPT_REFERENCE_STALE_TIPS): the reference's
 // computeApproximateMutation1 skips the tips a variable cannot move (forward_kinematics.h:940), so a probe scores those
@@ -75,14 +98,33 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
     const int unit = valid ? unit_raw : units - 1;
     const int q = STALE ? unit : (unit >> 1);
     const bool live = valid && !run_done(S, q, step) && S.memetic;
-    const int n = P.n, T = P.T, G = P.G, T7 = 7 * P.T;
+    const int n = P.n, T = P.T, G = P.G, T7 = 7 * P.T, K = P.tip_gene_start[P.T];
 
-    const GroupLayout L{n, T, G, W};
+    const GroupLayout L{n, T, G, W, K, STALE ? 1 : 0};
     double* Wk = smem + (size_t)(warp_in_block * GPW + gw) * L.total();
     double *ind = Wk + L.o_ind(), *graw = Wk + L.o_graw(), *grad = Wk + L.o_grad(), *ta = Wk + L.o_ta(), *tb = Wk + L.o_tb(), *base = Wk + L.o_base(), *clip = Wk + L.o_clip();
-    double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *gp = Wk + L.o_gp(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry();
-    int32_t* prev = (int32_t*)(Wk + L.o_prev());
+    double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *dxa = Wk + L.o_dxa(), *dxb = Wk + L.o_dxb();
+    double *gp = Wk + L.o_gp(), *gv = Wk + L.o_gv(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry();
+    int32_t* pair_start = (int32_t*)(Wk + L.o_int());
+    int32_t *pair_gene = pair_start + T + 1, *pair_of = pair_gene + K, *prev_pair = pair_of + T * n;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
+
+    // the pair lists of the problem, next to the data they index
+    if(live)
+    {
+        for(int t = gl; t <= T; t += W) pair_start[t] = P.tip_gene_start[t];
+        for(int k = gl; k < K; k += W) pair_gene[k] = P.tip_gene[k];
+        for(int k = gl; k < T * n; k += W) pair_of[k] = -1;
+    }
+    __syncwarp();
+    if(live)
+        for(int k = gl; k < K; k += W)
+        {
+            int t = 0;
+            while(pair_start[t + 1] <= k) t++;
+            pair_of[t * n + pair_gene[k]] = k;
+        }
+    __syncwarp();
     if(STALE && live)
     {
         for(int c = gl; c < T7; c += W) carry[c] = S.carry[(size_t)q * T7 + c];
@@ -90,8 +132,8 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
         {
             const int t = k / n, i = k - t * n;
             int j = i - 1;
-            while(j >= 0 && !((P.genes[j].tipmask >> t) & 1)) j--;
-            prev[k] = j;
+            while(j >= 0 && pair_of[t * n + j] < 0) j--;
+            prev_pair[k] = j >= 0 ? pair_of[t * n + j] : -1;
         }
     }
     for(int slot_it = 0; slot_it < (STALE ? 2 : 1); slot_it++)
@@ -117,7 +159,14 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
         const double* t0 = S.tip0 + (size_t)task * T * 7;
         for(int k = gl; k < T7; k += W) tip0[k] = t0[k];
         const double* d0 = S.delta + (size_t)task * T * n * 7;
-        for(int k = gl; k < T7 * n; k += W) delta[k] = d0[k];
+        for(int k = gl; k < 7 * K; k += W)
+        {
+            const int idx = k / 7, c = k - 7 * idx;
+            int t = 0;
+            while(pair_start[t + 1] <= idx) t++;
+            delta[k] = d0[((size_t)t * n + pair_gene[idx]) * 7 + c];
+        }
+        for(int idx = gl; idx < K; idx += W) dxa[idx] = gi[pair_gene[idx]] - b0[pair_gene[idx]]; // :1086
     }
     __syncwarp();
 
@@ -125,65 +174,92 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
     if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
     const bool quad = S.memetic == 'q';
 
-    // component c (= 7 t + k) of the full approximation of genotype x: the FMA chain of approx_frames_sparse
-    auto chain = [&](const double* x, int c) {
+    // component c (= 7 t + k) of the full approximation of a genotype x given as dx = x - base per pair: the FMA chain of
+    // approx_frames_sparse (the pairs of tip t in ascending gene order)
+    auto chain = [&](const double* dx, int c) {
         const int t = c / 7;
         double f = tip0[c];
-        const double* D = delta + (size_t)t * n * 7 + (c - 7 * t);
-        for(int i = 0; i < n; i++)
-        {
-            if(!((P.genes[i].tipmask >> t) & 1)) continue;
-            const double d = x[i] - base[i]; // :1086
-            f = BIOIK_FMA(d, D[7 * i], f);
-        }
+        const double* D = delta + (c - 7 * t);
+        const int i1 = pair_start[t + 1];
+        for(int idx = pair_start[t]; idx < i1; idx++) f = BIOIK_FMA(dx[idx], D[7 * idx], f);
         return f;
     };
-    // computeCombinedFitnessActiveVariables (src/ik_base.h:179-185) / computeFitnessActiveVariables
-    auto primary = [&](const double* frames, const double* x) { return goal_fitness_t(P, 0, (const double*)gp, frames, x, seed); };
-    auto combined = [&](const double* frames, const double* x) {
-        const double prim = primary(frames, x);
-        return prim + (P.has_secondary ? goal_fitness_secondary(P, (const double*)gp, x, seed) : 0.0);
+    // Goal::evaluate of goal g; secondary goals see the identity frames (src/ik_base.h:163)
+    auto goal_at = [&](int g, const double* frames, const double* x) {
+        const DGoal& go = P.goals[g];
+        return goal_value(P, go, (const double*)gp + g * GOAL_NPARAM, go.secondary ? (const double*)NULL_TIPS : frames, x, seed);
+    };
+    // the weighted sums of computeFitnessActiveVariables / computeCombinedFitnessActiveVariables (src/ik_base.h:179-185) over a
+    // row of goal values, in goal order
+    auto goal_sum = [&](int row, int which) {
+        double sum = 0.0;
+        for(int g = 0; g < G; g++)
+            if(P.goals[g].secondary == which) sum += gv[row * G + g] * P.goals[g].weight_sq;
+        return sum;
     };
 
     for(int generation = 0; generation < S.memetic_iters; generation++)
     {
         if(!__any_sync(FULL, alive)) break;
-        // (1) genotype = individual.genes -> phenotypes2 (:460-462)
-        if(alive)
-            for(int c = gl; c < T7; c += W) f2[c] = chain(ind, c);
-        __syncwarp();
-        // (2) f2p, fa (:463-464)
-        if(alive && gl == 0)
+        if(generation == 0)
         {
-            const double prim = primary(f2, ind);
-            sc[0] = prim;
-            sc[1] = prim + (P.has_secondary ? goal_fitness_secondary(P, (const double*)gp, (const double*)ind, seed) : 0.0);
+            // (1) genotype = individual.genes -> phenotypes2 (:460-462)
+            if(alive)
+                for(int c = gl; c < T7; c += W) f2[c] = chain(dxa, c);
+            __syncwarp();
+            // (2) f2p, fa (:463-464)
+            if(alive)
+                for(int g = gl; g < G; g += W) gv[g] = goal_at(g, f2, ind);
+            __syncwarp();
+            if(alive && gl == 0)
+            {
+                const double prim = goal_sum(0, 0);
+                sc[0] = prim;
+                sc[1] = prim + (P.has_secondary ? goal_sum(0, 1) : 0.0);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         // (3) gradient probes (:465-474): lane i moves variable i by dp
         if(alive)
         {
             const double fa = sc[1];
-            double* ph3 = pl + gl * T7;
             for(int i = gl; i < n; i += W)
             {
-                for(int t = 0; t < T; t++)
-                {
-                    const double* D = delta + ((size_t)t * n + i) * 7;
-                    if(STALE && !((P.genes[i].tipmask >> t) & 1))
-                    {
-                        // the tip keeps what the buffer held: the write of the last earlier probe that moves it, else the carried frame
-                        const int j = prev[t * n + i];
-                        const double* Dj = delta + ((size_t)t * n + (j >= 0 ? j : 0)) * 7;
-                        for(int k = 0; k < 7; k++) ph3[7 * t + k] = j >= 0 ? BIOIK_FMA(dp, Dj[k], f2[7 * t + k]) : carry[7 * t + k];
-                        continue;
-                    }
-                    for(int k = 0; k < 7; k++) ph3[7 * t + k] = BIOIK_FMA(dp, D[k], f2[7 * t + k]); // :469
-                }
                 const ProbeGenes x{ind, i, ind[i] + dp}; // :468
-                const double prim = goal_fitness_t(P, 0, (const double*)gp, (const double*)ph3, x, seed);
-                const double comb = prim + (P.has_secondary ? goal_fitness_secondary(P, (const double*)gp, x, seed) : 0.0);
-                graw[i] = comb - fa; // :472-473
+                double prim = 0.0, sec = 0.0;
+                for(int g = 0; g < G; g++)
+                {
+                    const DGoal& go = P.goals[g];
+                    double v;
+                    if(is_joint_goal(go.type))
+                        v = goal_value(P, go, (const double*)gp + g * GOAL_NPARAM, (const double*)NULL_TIPS, x, seed);
+                    else if(go.secondary)
+                        v = gv[g]; // a link goal on the identity frames: what it is for the current genes
+                    else
+                    {
+                        // :469 for the tip of this goal
+                        const int t = go.tip;
+                        int pi = pair_of[t * n + i];
+                        double fr[7];
+                        if(!STALE)
+                        {
+                            // a tip the variable cannot move stays where the current genes put it (its delta frame is zero)
+                            for(int k = 0; k < 7; k++) fr[k] = pi >= 0 ? BIOIK_FMA(dp, delta[7 * pi + k], f2[7 * t + k]) : f2[7 * t + k];
+                        }
+                        else
+                        {
+                            // the tip keeps what the buffer held: the write of the last earlier probe that moves it, else the carried frame
+                            if(pi < 0) pi = prev_pair[t * n + i];
+                            for(int k = 0; k < 7; k++) fr[k] = pi >= 0 ? BIOIK_FMA(dp, delta[7 * pi + k], f2[7 * t + k]) : carry[7 * t + k];
+                        }
+                        v = goal_value(P, go, (const double*)gp + g * GOAL_NPARAM, ProbeFrame{fr}, x, seed);
+                    }
+                    if(go.secondary)
+                        sec += v * go.weight_sq;
+                    else
+                        prim += v * go.weight_sq;
+                }
+                graw[i] = (prim + (P.has_secondary ? sec : 0.0)) - fa; // :472-473
             }
         }
         __syncwarp();
@@ -200,19 +276,32 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
                 ta[i] = ind[i] - g;
                 tb[i] = ind[i] + g;
             }
+            for(int idx = gl; idx < K; idx += W)
+            {
+                const int i = pair_gene[idx];
+                const double g = graw[i] * f;
+                dxa[idx] = (ind[i] - g) - base[i]; // :1086
+                dxb[idx] = (ind[i] + g) - base[i];
+            }
         }
         __syncwarp();
-        // (5) both support points -> frames (rows 0 and 1 of the per-lane frame block)
+        // (5) both support points -> frames
         if(alive)
             for(int c = gl; c < 2 * T7; c += W)
             {
                 const int which = c >= T7 ? 1 : 0;
-                const int cc = c - which * T7;
-                pl[which * T7 + cc] = chain(which ? tb : ta, cc);
+                pl[c] = chain(which ? dxb : dxa, c - which * T7);
             }
         __syncwarp();
         // (6) f1, f3 (:487-488, :494-495)
-        if(alive && gl < 2) sc[2 + gl] = combined(pl + gl * T7, gl ? tb : ta);
+        if(alive)
+            for(int item = gl; item < 2 * G; item += W)
+            {
+                const int which = item >= G ? 1 : 0;
+                gv[G + item] = goal_at(item - which * G, pl + which * T7, which ? tb : ta);
+            }
+        __syncwarp();
+        if(alive && gl < 2) sc[2 + gl] = goal_sum(1 + gl, 0) + (P.has_secondary ? goal_sum(1 + gl, 1) : 0.0);
         __syncwarp();
         // (7) step size and the candidate (:502-506,:525 / :549-554)
         if(alive)
@@ -220,35 +309,61 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             if(STALE)
                 for(int c = gl; c < T7; c += W) carry[c] = pl[T7 + c]; // phenotypes3 now holds the frames of the f3 evaluation (:494)
             const double f2v = sc[1], f1 = sc[2], f3 = sc[3];
+            double step_size;
             if(quad)
             {
                 double v1 = (f2v - f1);
                 double v2 = (f3 - f2v);
                 double v = (v1 + v2) * 0.5;
                 double a = (v1 - v2);
-                double step_size = v / a;
+                step_size = v / a;
                 for(int i = gl; i < n; i += W) ta[i] = clampd(ind[i] + grad[i] * step_size * 1.0, clip[2 * i], clip[2 * i + 1]);
+                for(int idx = gl; idx < K; idx += W)
+                {
+                    const int i = pair_gene[idx];
+                    dxa[idx] = clampd(ind[i] + grad[i] * step_size * 1.0, clip[2 * i], clip[2 * i + 1]) - base[i];
+                }
             }
             else
             {
                 double cost_diff = (f3 - f1) * 0.5;
-                double step_size = f2v / cost_diff;
+                step_size = f2v / cost_diff;
                 for(int i = gl; i < n; i += W) ta[i] = clampd(ind[i] - grad[i] * step_size, clip[2 * i], clip[2 * i + 1]);
+                for(int idx = gl; idx < K; idx += W)
+                {
+                    const int i = pair_gene[idx];
+                    dxa[idx] = clampd(ind[i] - grad[i] * step_size, clip[2 * i], clip[2 * i + 1]) - base[i];
+                }
             }
         }
         __syncwarp();
         // (8) candidate -> phenotypes2 (:526 / :555)
         if(alive)
-            for(int c = gl; c < T7; c += W) f2[c] = chain(ta, c);
+            for(int c = gl; c < T7; c += W) f2[c] = chain(dxa, c);
         __syncwarp();
-        // (9) f4p
-        if(alive && gl == 0) sc[4] = primary(f2, ta);
+        // (9) f4p - and the candidate's secondary goals: if it is accepted they are the next iteration's fa
+        if(alive)
+            for(int g = gl; g < G; g += W) gv[G + g] = goal_at(g, f2, ta);
+        __syncwarp();
+        if(alive && gl == 0) sc[4] = goal_sum(1, 0);
         __syncwarp();
         // (10) accept / stop (:530-538 / :559-567)
+        bool accept = false;
+        if(alive) accept = sc[4] < sc[0];
+        __syncwarp();
         if(alive)
         {
-            if(sc[4] < sc[0])
+            if(accept)
+            {
+                // individual.genes = candidate: phenotypes2, f2p and fa of the next iteration (:460-464) are the candidate's
                 for(int i = gl; i < n; i += W) ind[i] = ta[i];
+                for(int g = gl; g < G; g += W) gv[g] = gv[G + g];
+                if(gl == 0)
+                {
+                    sc[0] = sc[4];
+                    sc[1] = sc[4] + (P.has_secondary ? goal_sum(1, 1) : 0.0);
+                }
+            }
             else
                 alive = false;
         }
