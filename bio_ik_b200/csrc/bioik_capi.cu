@@ -448,7 +448,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
         R.mgk = select_memetic_group(R.mg_width, R.stale);
         R.mg_warps = 4;
         const int mg_tasks_per_block = R.mg_warps * (32 / R.mg_width);
-        const GroupLayout mgl{P.n, P.T, P.G, R.mg_width, P.tip_gene_start[P.T], R.stale ? 1 : 0};
+        const GroupLayout mgl{P.n, P.T, P.G, R.mg_width, P.tip_gene_start[P.T], R.stale ? 1 : 0, P.n_joint_goals};
         R.mg_smem = (size_t)mg_tasks_per_block * mgl.total() * sizeof(double);
         // the unrolled single-pose path of k_serial issues ~3x fewer instructions per task than a lane group; everything else
         // gains from the extra parallelism of the group kernel

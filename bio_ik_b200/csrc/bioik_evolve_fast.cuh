@@ -67,7 +67,7 @@ __global__ void k_mutation_table(const DProblem* __restrict__ Pp, int calls, int
 // per-warp shared-memory carve-up (doubles); every block is 16-byte aligned
 struct FastSmem
 {
-    int n, T, G, nj;
+    int n, T, G, nj; // nj = joint-space goals of the problem (0: no joint records)
     int lean = 0; // 1: no per-child fitness arrays (only the pre-selection of problems with secondary goals reads them)
     int pairs = 0; // tip-major form: the delta frames of the (tip, gene) pairs of DProblem::tip_gene only, in list order (0: dense [T][n])
     __host__ __device__ int off_rec() const { return 0; }                        // [n][4]  g0, base, clip_min, clip_max
@@ -79,7 +79,7 @@ struct FastSmem
     __host__ __device__ int off_gp() const { return off_tip0() + 8 * T; }        // [G][12]
     __host__ __device__ int off_jrec() const { return off_gp() + 12 * G; }       // [n][4]  mid, halfspan, vel_weight, seed  (nj > 0)
     __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
-    __host__ __device__ int off_fit() const { return off_jq() + (nj ? 4 * FAST_MAX_JOINT_GOALS * n : 0); } // [256] primary fitness per child slot
+    __host__ __device__ int off_fit() const { return off_jq() + 4 * nj * n; } // [256] primary fitness per child slot
     __host__ __device__ int off_sf() const { return off_fit() + (lean ? 0 : 256); }   // [256] secondary fitness per child slot
     __host__ __device__ int total() const { return ((off_sf() + (lean ? 0 : 256)) + 1) & ~1; }
 };
@@ -89,7 +89,7 @@ __host__ __device__ inline bool fast_tip_major(const DProblem& P) { return P.T >
 // the shared-memory plan of one task of the generation kernel select_evolve_fast picks for P
 __host__ __device__ inline FastSmem fast_smem_layout(const DProblem& P)
 {
-    return FastSmem{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1, fast_tip_major(P) ? P.tip_gene_start[P.T] : 0};
+    return FastSmem{P.n, P.T, P.G, P.n_joint_goals, P.has_secondary ? 0 : 1, fast_tip_major(P) ? P.tip_gene_start[P.T] : 0};
 }
 
 template <int T> BIOIK_HD void select_frame(const double (&F)[T][7], int tip, double* f)
@@ -378,7 +378,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 nj++;
             }
 
-    FastSmem L{n, TM ? P.T : T, G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
+    FastSmem L{n, TM ? P.T : T, G, JOINT ? P.n_joint_goals : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
     const int TT = TM ? P.T : T; // tips of the problem
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
     double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
@@ -1023,7 +1023,7 @@ template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int
     const int warp_in_block = threadIdx.x >> 5;
     const int task = (blockIdx.x * (blockDim.x >> 5) + warp_in_block) * TPW + grp;
     const int n = NG ? NG : P.n;
-    FastSmem L{n, TM ? P.T : T, P.G, JOINT ? 1 : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
+    FastSmem L{n, TM ? P.T : T, P.G, JOINT ? P.n_joint_goals : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
     evolve_fast_task<T, CH, GSPEC, JOINT, NG, TM, LPT>(P, S, step, mtab, smem + (size_t)(warp_in_block * TPW + grp) * L.total(), task, lane, lane0, gmask);
 }
 

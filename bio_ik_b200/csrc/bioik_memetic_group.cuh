@@ -20,6 +20,36 @@
 namespace bioik
 {
 
+// The joint-space goals that are a sum over the active variables (goal_types.h:387-465): sum = 0, then sum += term(gene)
+// for every gene the goal applies to, in gene order.  term() is the loop body of goal_value's case, operation for operation.
+BIOIK_HD bool is_summing_joint_goal(int type) { return type == G_AVOID_JOINT_LIMITS || type == G_CENTER_JOINTS || type == G_REGULARIZATION || type == G_MINIMAL_DISPLACEMENT; }
+BIOIK_HD bool joint_term_applies(const DProblem& P, int type, int i) { return (type == G_AVOID_JOINT_LIMITS || type == G_CENTER_JOINTS) ? P.genes[i].clip_max != DBLMAX : true; }
+BIOIK_HD double joint_term(const DProblem& P, int type, int i, double x, const double* seed)
+{
+    const DGene& Gn = P.genes[i];
+    double d;
+    switch(type)
+    {
+    case G_AVOID_JOINT_LIMITS: // goal_types.h:387-401
+        d = x - (Gn.vmin + Gn.vmax) * 0.5;
+        d = BIOIK_FMAX(0.0, BIOIK_FABS(d) * 2.0 - Gn.span * 0.5);
+        d *= Gn.vel_weight;
+        break;
+    case G_CENTER_JOINTS: // goal_types.h:412-425
+        d = x - (Gn.vmin + Gn.vmax) * 0.5;
+        d *= Gn.vel_weight;
+        break;
+    case G_REGULARIZATION: // goal_types.h:435-444
+        d = x - seed[Gn.var];
+        break;
+    default: // G_MINIMAL_DISPLACEMENT, goal_types.h:455-465
+        d = x - seed[Gn.var];
+        d *= Gn.vel_weight;
+        break;
+    }
+    return d * d;
+}
+
 // genes of a probe: individual.genes with element i replaced (ik_evolution_2.cpp:468-471)
 struct ProbeGenes
 {
@@ -41,7 +71,7 @@ struct ProbeFrame
 // (DProblem::tip_gene; every other delta frame is all zero and never read)
 struct GroupLayout
 {
-    int n, T, G, W, K, stale;
+    int n, T, G, W, K, stale, NJ; // NJ = joint-space goals of the problem (an upper bound of the summing ones)
     __host__ __device__ int o_ind() const { return 0; }
     __host__ __device__ int o_graw() const { return n; }
     __host__ __device__ int o_grad() const { return 2 * n; }
@@ -59,10 +89,11 @@ struct GroupLayout
     __host__ __device__ int o_gv() const { return o_gp() + GOAL_NPARAM * G; } // [3][G] goal values: current genes; support point a / candidate; support point b
     __host__ __device__ int o_sc() const { return o_gv() + 3 * G; }
     __host__ __device__ int o_carry() const { return o_sc() + 8; }               // [7T] reference-quirk mode: the frames left in phenotypes3
-    __host__ __device__ int o_int() const { return o_carry() + (stale ? 7 * T : 0); }
-    // int32: pair_start [T + 1], pair_gene [K], pair_of [T][n] (-1: the gene cannot move the tip); reference-quirk mode:
-    // prev_pair [T][n] = pair of the last earlier gene that moves tip t (-1: none)
-    __host__ __device__ int ints() const { return T + 1 + K + T * n + (stale ? T * n : 0); }
+    __host__ __device__ int o_jt() const { return o_carry() + (stale ? 7 * T : 0); } // [3][NJ][n] terms of the summing joint-space goals, rows as gv
+    __host__ __device__ int o_int() const { return o_jt() + 3 * NJ * n; }
+    // int32: pair_start [T + 1], pair_gene [K], pair_of [T][n] (-1: the gene cannot move the tip), sum_slot [G] (row of jt, -1: not a
+    // summing joint-space goal); reference-quirk mode: prev_pair [T][n] = pair of the last earlier gene that moves tip t (-1: none)
+    __host__ __device__ int ints() const { return T + 1 + K + T * n + G + (stale ? T * n : 0); }
     __host__ __device__ int total() const { return (o_int() + (ints() + 1) / 2) | 1; } // odd stride: the groups of a warp start in different banks
 };
 
@@ -75,6 +106,8 @@ inline int memetic_group_width(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 //     per pair by the phase that produces x;
 //   * Goal::evaluate of every goal on its own lane, then the weighted sum in goal order on one lane (src/problem.cpp:251-257);
 //   * a probe builds the one frame each link goal reads in registers (computeApproximateMutation1 of ONE variable);
+//   * a joint-space goal that sums over the variables has its terms formed by the lane of each variable where the variable's
+//     value is produced; the evaluation is the ordered sum of the stored terms (a probe substitutes its one term);
 //   * the candidate of an accepted iteration IS the next iteration's individual: its frames and goal values (f4p, and the
 //     secondary goals for fa) are kept instead of being recomputed by (1) and (2).
 //
@@ -100,14 +133,20 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
     const bool live = valid && !run_done(S, q, step) && S.memetic;
     const int n = P.n, T = P.T, G = P.G, T7 = 7 * P.T, K = P.tip_gene_start[P.T];
 
-    const GroupLayout L{n, T, G, W, K, STALE ? 1 : 0};
+    const GroupLayout L{n, T, G, W, K, STALE ? 1 : 0, P.n_joint_goals};
+    const int NJ = P.n_joint_goals;
     double* Wk = smem + (size_t)(warp_in_block * GPW + gw) * L.total();
     double *ind = Wk + L.o_ind(), *graw = Wk + L.o_graw(), *grad = Wk + L.o_grad(), *ta = Wk + L.o_ta(), *tb = Wk + L.o_tb(), *base = Wk + L.o_base(), *clip = Wk + L.o_clip();
     double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *dxa = Wk + L.o_dxa(), *dxb = Wk + L.o_dxb();
-    double *gp = Wk + L.o_gp(), *gv = Wk + L.o_gv(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry();
+    double *gp = Wk + L.o_gp(), *gv = Wk + L.o_gv(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry(), *jt = Wk + L.o_jt();
     int32_t* pair_start = (int32_t*)(Wk + L.o_int());
-    int32_t *pair_gene = pair_start + T + 1, *pair_of = pair_gene + K, *prev_pair = pair_of + T * n;
+    int32_t *pair_gene = pair_start + T + 1, *pair_of = pair_gene + K, *sum_slot = pair_of + T * n, *prev_pair = sum_slot + G;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
+    // terms of the summing joint-space goals for gene i at value x -> row of jt
+    auto store_terms = [&](int row, int i, double x) {
+        for(int g = 0; g < G; g++)
+            if(sum_slot[g] >= 0) jt[((size_t)row * NJ + sum_slot[g]) * n + i] = joint_term(P, P.goals[g].type, i, x, seed);
+    };
 
     // the pair lists of the problem, next to the data they index
     if(live)
@@ -115,6 +154,12 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
         for(int t = gl; t <= T; t += W) pair_start[t] = P.tip_gene_start[t];
         for(int k = gl; k < K; k += W) pair_gene[k] = P.tip_gene[k];
         for(int k = gl; k < T * n; k += W) pair_of[k] = -1;
+        for(int g = gl; g < G; g += W)
+        {
+            int slot = 0;
+            for(int h = 0; h < g; h++) slot += is_summing_joint_goal(P.goals[h].type) ? 1 : 0;
+            sum_slot[g] = is_summing_joint_goal(P.goals[g].type) ? slot : -1;
+        }
     }
     __syncwarp();
     if(live)
@@ -167,6 +212,8 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             delta[k] = d0[((size_t)t * n + pair_gene[idx]) * 7 + c];
         }
         for(int idx = gl; idx < K; idx += W) dxa[idx] = gi[pair_gene[idx]] - b0[pair_gene[idx]]; // :1086
+        if(NJ)
+            for(int i = gl; i < n; i += W) store_terms(0, i, gi[i]);
     }
     __syncwarp();
 
@@ -184,9 +231,19 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
         for(int idx = pair_start[t]; idx < i1; idx++) f = BIOIK_FMA(dx[idx], D[7 * idx], f);
         return f;
     };
-    // Goal::evaluate of goal g; secondary goals see the identity frames (src/ik_base.h:163)
-    auto goal_at = [&](int g, const double* frames, const double* x) {
+    // Goal::evaluate of goal g for the genes x whose terms are in row `row` of jt; secondary goals see the identity frames
+    // (src/ik_base.h:163)
+    auto goal_at = [&](int g, const double* frames, const double* x, int row) {
         const DGoal& go = P.goals[g];
+        const int slot = sum_slot[g];
+        if(slot >= 0)
+        {
+            const double* t = jt + ((size_t)row * NJ + slot) * n;
+            double sum = 0.0;
+            for(int i = 0; i < n; i++)
+                if(joint_term_applies(P, go.type, i)) sum += t[i];
+            return sum;
+        }
         return goal_value(P, go, (const double*)gp + g * GOAL_NPARAM, go.secondary ? (const double*)NULL_TIPS : frames, x, seed);
     };
     // the weighted sums of computeFitnessActiveVariables / computeCombinedFitnessActiveVariables (src/ik_base.h:179-185) over a
@@ -209,7 +266,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             __syncwarp();
             // (2) f2p, fa (:463-464)
             if(alive)
-                for(int g = gl; g < G; g += W) gv[g] = goal_at(g, f2, ind);
+                for(int g = gl; g < G; g += W) gv[g] = goal_at(g, f2, ind, 0);
             __syncwarp();
             if(alive && gl == 0)
             {
@@ -231,7 +288,17 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
                 {
                     const DGoal& go = P.goals[g];
                     double v;
-                    if(is_joint_goal(go.type))
+                    if(sum_slot[g] >= 0)
+                    {
+                        // the stored terms of the current genes with this variable's term replaced
+                        const double* t = jt + (size_t)sum_slot[g] * n;
+                        const double mine = joint_term(P, go.type, i, x.v, seed);
+                        double sum = 0.0;
+                        for(int j = 0; j < n; j++)
+                            if(joint_term_applies(P, go.type, j)) sum += j == i ? mine : t[j];
+                        v = sum;
+                    }
+                    else if(is_joint_goal(go.type))
                         v = goal_value(P, go, (const double*)gp + g * GOAL_NPARAM, (const double*)NULL_TIPS, x, seed);
                     else if(go.secondary)
                         v = gv[g]; // a link goal on the identity frames: what it is for the current genes
@@ -275,6 +342,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
                 grad[i] = g;
                 ta[i] = ind[i] - g;
                 tb[i] = ind[i] + g;
+                if(NJ) store_terms(1, i, ind[i] - g), store_terms(2, i, ind[i] + g);
             }
             for(int idx = gl; idx < K; idx += W)
             {
@@ -298,7 +366,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             for(int item = gl; item < 2 * G; item += W)
             {
                 const int which = item >= G ? 1 : 0;
-                gv[G + item] = goal_at(item - which * G, pl + which * T7, which ? tb : ta);
+                gv[G + item] = goal_at(item - which * G, pl + which * T7, which ? tb : ta, 1 + which);
             }
         __syncwarp();
         if(alive && gl < 2) sc[2 + gl] = goal_sum(1 + gl, 0) + (P.has_secondary ? goal_sum(1 + gl, 1) : 0.0);
@@ -317,7 +385,11 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
                 double v = (v1 + v2) * 0.5;
                 double a = (v1 - v2);
                 step_size = v / a;
-                for(int i = gl; i < n; i += W) ta[i] = clampd(ind[i] + grad[i] * step_size * 1.0, clip[2 * i], clip[2 * i + 1]);
+                for(int i = gl; i < n; i += W)
+                {
+                    ta[i] = clampd(ind[i] + grad[i] * step_size * 1.0, clip[2 * i], clip[2 * i + 1]);
+                    if(NJ) store_terms(1, i, ta[i]);
+                }
                 for(int idx = gl; idx < K; idx += W)
                 {
                     const int i = pair_gene[idx];
@@ -328,7 +400,11 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             {
                 double cost_diff = (f3 - f1) * 0.5;
                 step_size = f2v / cost_diff;
-                for(int i = gl; i < n; i += W) ta[i] = clampd(ind[i] - grad[i] * step_size, clip[2 * i], clip[2 * i + 1]);
+                for(int i = gl; i < n; i += W)
+                {
+                    ta[i] = clampd(ind[i] - grad[i] * step_size, clip[2 * i], clip[2 * i + 1]);
+                    if(NJ) store_terms(1, i, ta[i]);
+                }
                 for(int idx = gl; idx < K; idx += W)
                 {
                     const int i = pair_gene[idx];
@@ -343,7 +419,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
         __syncwarp();
         // (9) f4p - and the candidate's secondary goals: if it is accepted they are the next iteration's fa
         if(alive)
-            for(int g = gl; g < G; g += W) gv[G + g] = goal_at(g, f2, ta);
+            for(int g = gl; g < G; g += W) gv[G + g] = goal_at(g, f2, ta, 1);
         __syncwarp();
         if(alive && gl == 0) sc[4] = goal_sum(1, 0);
         __syncwarp();
@@ -357,6 +433,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_me
             {
                 // individual.genes = candidate: phenotypes2, f2p and fa of the next iteration (:460-464) are the candidate's
                 for(int i = gl; i < n; i += W) ind[i] = ta[i];
+                for(int k = gl; k < NJ * n; k += W) jt[k] = jt[NJ * n + k];
                 for(int g = gl; g < G; g += W) gv[g] = gv[G + g];
                 if(gl == 0)
                 {

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(32 * PERSIST_WARPS, 4) k_persist(BIOIK_PROBLEM
     const unsigned gmask = ((1u << LPT) - 1u) << lane0;
     const DProblem& Pg = *Pp; // the generation body indexes the problem per lane: global memory, not the constant bank
     const int n = NG ? NG : Pg.n;
-    FastSmem L{n, TM ? Pg.T : T, Pg.G, JOINT ? 1 : 0, Pg.has_secondary ? 0 : 1};
+    FastSmem L{n, TM ? Pg.T : T, Pg.G, JOINT ? Pg.n_joint_goals : 0, Pg.has_secondary ? 0 : 1};
     double* ev = smem + (size_t)(warp * TPW + grp) * L.total();
     double* ser = smem + (size_t)PERSIST_WARPS * TPW * L.total();
     const bool serial_warp = warp == (int)((blockIdx.x / (unsigned)max(A.sm_count, 1)) % PERSIST_WARPS) || blockDim.x < 32 * PERSIST_WARPS;
@@ -238,7 +238,7 @@ typedef void (*PersistKernel)(const DProblem, const DProblem*, DState, PersistAr
 // shared memory of one block of the persistent kernel for problem P (bytes); *ser_doubles = offset of the serial region
 inline size_t persist_smem_bytes(const DProblem& P, int lpt, bool delta_smem, bool frames_smem)
 {
-    FastSmem L{P.n, P.T, P.G, P.n_joint_goals > 0 ? 1 : 0, P.has_secondary ? 0 : 1};
+    FastSmem L = fast_smem_layout(P);
     const size_t ev = (size_t)PERSIST_WARPS * (32 / lpt) * L.total();
     const size_t ser = (size_t)(serial_fixed_doubles(P) + (delta_smem ? 7 * P.T * P.n : 0) + (frames_smem ? 7 * P.L : 0)) * 32;
     return (ev + ser) * sizeof(double);
