@@ -39,6 +39,8 @@ static inline double bioik_clear_low_word(double s)
     return s;
 }
 #define BIOIK_CLEAR_LOW_WORD(s) bioik_clear_low_word(s)
+static inline double bioik_sel_gt0(double c, double a, double b) { return c > 0.0 ? a : b; }
+static inline double bioik_sel_ne0(double c, double a, double b) { return c != 0.0 ? a : b; }
 #else
 #define BIOIK_HD __device__ __forceinline__
 #define BIOIK_FMA(a, b, c) __fma_rn((a), (b), (c))
@@ -53,6 +55,20 @@ static inline double bioik_clear_low_word(double s)
 #define BIOIK_ATAN2(a, b) atan2((a), (b))
 #define BIOIK_ACOS(a) acos(a)
 #define BIOIK_CLEAR_LOW_WORD(s) __hiloint2double(__double2hiint(s), 0)
+// c > 0 ? a : b and c != 0 ? a : b as SELECT instructions (false for a NaN c): left to itself the compiler turns such an
+// expression on per-lane data into a divergent branch
+__device__ __forceinline__ double bioik_sel_gt0(double c, double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %2, %3, p;\n\t}" : "=d"(r) : "d"(c), "d"(a), "d"(b));
+    return r;
+}
+__device__ __forceinline__ double bioik_sel_ne0(double c, double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %2, %3, p;\n\t}" : "=d"(r) : "d"(c), "d"(a), "d"(b));
+    return r;
+}
 #endif
 
 namespace bioik

@@ -169,6 +169,21 @@ BIOIK_HD double link_goal_value(int type, const double* p, const double* f)
 
 BIOIK_HD bool is_joint_goal(int type) { return type >= G_AVOID_JOINT_LIMITS && type <= G_JOINT_VARIABLE; }
 
+// what one gene adds to a joint-space goal, from its record r = {centre, half span, weight, applies}: the term of
+// joint_goal_accumulate, or +0.0 where the goal does not apply to the gene (branch-free: acc + 0.0 == acc, the accumulators
+// are never -0).  max(0, y) as a select: fmax(0.0, y) for every y up to the sign of a zero, which the square drops.
+BIOIK_HD double joint_record_term(const double* r, bool avoid, double x)
+{
+    double dd = x - r[0];
+    if(avoid)
+    {
+        const double y = BIOIK_FABS(dd) * 2.0 - r[1];
+        dd = bioik_sel_gt0(y, y, 0.0);
+    }
+    dd *= r[2];
+    return bioik_sel_ne0(r[3], dd * dd, 0.0);
+}
+
 // one gene's contribution to a joint-space goal (goal_types.h:387-465,494-498), gene order = loop order
 BIOIK_HD void joint_goal_accumulate(int type, int var_index, int i, double x, double clip_max, double mid, double halfspan, double vw, double seedv, double p0, double& acc)
 {
@@ -554,18 +569,8 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                             if(j < nj)
                             {
                                 const double* r = s_jq + ((size_t)j * n + i) * 4;
-                                if(r[3] != 0.0)
-                                {
-                                    const double c = r[0], hs = r[1], w = r[2];
 #pragma unroll
-                                    for(int k = 0; k < CH; k++)
-                                    {
-                                        double dd = x[k] - c;
-                                        if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
-                                        dd *= w;
-                                        acc[k][j] += dd * dd;
-                                    }
-                                }
+                                for(int k = 0; k < CH; k++) acc[k][j] += joint_record_term(r, jq_avoid[j], x[k]);
                             }
                     }
                 // weighted sums in goal order (src/problem.cpp:251-257): a link goal finds its tip's frames in F (kept while
@@ -725,18 +730,8 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                             if(j < nj)
                             {
                                 const double* r = s_jq + ((size_t)j * n + i) * 4;
-                                if(r[3] != 0.0) // warp-uniform: the goal applies to this gene
-                                {
-                                    const double c = r[0], hs = r[1], w = r[2];
     #pragma unroll
-                                    for(int k = 0; k < CH; k++)
-                                    {
-                                        double dd = x[k] - c;
-                                        if(jq_avoid[j]) dd = BIOIK_FMAX(0.0, BIOIK_FABS(dd) * 2.0 - hs);
-                                        dd *= w;
-                                        acc[k][j] += dd * dd;
-                                    }
-                                }
+                                for(int k = 0; k < CH; k++) acc[k][j] += joint_record_term(r, jq_avoid[j], x[k]);
                             }
                     }
                 };
@@ -873,31 +868,36 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
             __syncwarp(gmask);
-            // the lane's children four at a time: one broadcast read of every other child's secondary fitness serves four ranks
-#pragma unroll 1
-            for(int k0 = 0; k0 < FAST_MAX_CPL; k0 += 4)
-            {
-                if(lane + 32 * k0 >= C) break;
-                double mine[4];
-                int rank[4];
+            // the lane's children c0, c0 + 32, ... (c0 = its first child slot >= 2), NB at a time: one broadcast read of every
+            // other child's secondary fitness serves NB ranks
+            const int c0 = lane < 2 ? lane + 32 : lane;
+            auto rank_block = [&](auto nb_tag, int j0) {
+                constexpr int NB = decltype(nb_tag)::value;
+                double mine[NB];
+                int rank[NB];
 #pragma unroll
-                for(int j = 0; j < 4; j++)
+                for(int j = 0; j < NB; j++)
                 {
-                    const int c = lane + 32 * (k0 + j);
-                    mine[j] = (c >= 2 && c < C) ? s_sf[c] : 0.0;
+                    const int c = c0 + 32 * (j0 + j);
+                    mine[j] = c < C ? s_sf[c] : 0.0;
                     rank[j] = 0;
                 }
                 for(int o = 2; o < C; o++)
                 {
                     const double other = s_sf[o];
 #pragma unroll
-                    for(int j = 0; j < 4; j++) rank[j] += (other < mine[j] || (other == mine[j] && o < lane + 32 * (k0 + j))) ? 1 : 0;
+                    for(int j = 0; j < NB; j++)
+                    {
+                        // no short-circuit: evaluated as predicate logic, not as data-dependent (divergent) branches
+                        const int lt = other < mine[j] ? 1 : 0, eq = other == mine[j] ? 1 : 0, before = o < c0 + 32 * (j0 + j) ? 1 : 0;
+                        rank[j] += lt | (eq & before);
+                    }
                 }
 #pragma unroll
-                for(int j = 0; j < 4; j++)
+                for(int j = 0; j < NB; j++)
                 {
-                    const int c = lane + 32 * (k0 + j);
-                    if(c < 2 || c >= C) continue;
+                    const int c = c0 + 32 * (j0 + j);
+                    if(c >= C) continue;
                     if(2 + rank[j] >= child_count) continue;
                     uint64_t kk = fast_fitness_key(s_fit[c]);
                     uint32_t pk = (uint32_t)(2 + rank[j]) * 512u + (uint32_t)c;
@@ -911,6 +911,14 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                         k2 = kk; q2 = pk;
                     }
                 }
+            };
+            const int per_lane = (C - 2 + 31) / 32; // children of the busiest lane
+            if(per_lane <= 2)
+                rank_block(std::integral_constant<int, 2>{}, 0);
+            else
+            {
+#pragma unroll 1
+                for(int j0 = 0; j0 < per_lane; j0 += 4) rank_block(std::integral_constant<int, 4>{}, j0);
             }
         }
 

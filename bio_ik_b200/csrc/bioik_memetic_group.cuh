@@ -118,7 +118,12 @@ inline int memetic_group_width(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 // phenotypes3 and treats species 0, then species 1), or of the previous step.  Here a group owns a QUERY, runs its two
 // species one after the other and carries those frames in `carry` (HBM between steps; identity frames at the start, which
 // is what the harness of the reference build pre-fills - a fresh reference solver reads uninitialised memory there).
-template <int W, bool STALE = false> __global__ void __launch_bounds__(128) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
+// blocks per SM the register allocation aims for: the kernel is a chain of short dependent phases (latency-bound), so more
+// resident warps beat a larger register file per thread (80 registers, no spills; measured: profiles/r02_experiments.md)
+#ifndef BIOIK_MG_MINBLOCKS
+#define BIOIK_MG_MINBLOCKS 6
+#endif
+template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOIK_MG_MINBLOCKS) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
 {
     extern __shared__ double smem[];
     constexpr int GPW = 32 / W;

@@ -122,7 +122,8 @@ def test_generation_kernel_lane_groups(sim, oracle, lanes):
 
 
 @pytest.mark.parametrize("name,B,pop,mode,steps,variant", [("cfg2", 3, 18, "q", 4, 6), ("cfg2", 3, 40, "l", 3, 6), ("cfg2", 3, 18, "q", 3, 9), ("cfg3", 3, 40, "q", 3, 6), ("cfg3", 1, 20, "q", 2, 7),
-                                                            ("cfg4", 2, 40, "q", 2, 6), ("cfg4", 1, 20, "l", 2, 8), ("cfg5", 3, 36, "q", 2, 6), ("cfg5", 1, 20, "q", 2, 7)])
+                                                            ("cfg4", 2, 40, "q", 2, 6), ("cfg4", 1, 20, "l", 2, 8), ("cfg5", 3, 36, "q", 2, 6), ("cfg5", 1, 20, "q", 2, 7),
+                                                            ("cfg4", 1, 128, "q", 2, 6), ("cfg4", 1, 210, "q", 1, 6)])
 def test_group_memetic_kernel(sim, oracle, name, B, pop, mode, steps, variant):
     """k_memetic_group: the memetic line search on W lanes per task (6 = the width the library picks, 7/8/9 = W forced
     to 8/16/32, so every problem also runs with more variables than lanes and with idle lanes); odd task counts leave
