@@ -85,7 +85,10 @@ struct FastSmem
 };
 
 // problems with three or more tips run the tip-major form of the generation kernel (select_evolve_fast)
-__host__ __device__ inline bool fast_tip_major(const DProblem& P) { return P.T > 2; }
+#ifndef BIOIK_TM_MIN_TIPS
+#define BIOIK_TM_MIN_TIPS 3
+#endif
+__host__ __device__ inline bool fast_tip_major(const DProblem& P) { return P.T >= BIOIK_TM_MIN_TIPS; }
 // the shared-memory plan of one task of the generation kernel select_evolve_fast picks for P
 __host__ __device__ inline FastSmem fast_smem_layout(const DProblem& P)
 {
