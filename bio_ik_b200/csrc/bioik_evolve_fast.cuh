@@ -871,17 +871,22 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
             __syncwarp(gmask);
-            // the lane's children c0, c0 + 32, ... (c0 = its first child slot >= 2), NB at a time: one broadcast read of every
-            // other child's secondary fitness serves NB ranks
+            // the lane's children c0, c0 + 32, ... (c0 = its first child slot >= 2), all NB of them together: one broadcast read of
+            // every other child's secondary fitness serves NB ranks.
+            // Fast pass: rank' = how many children have a strictly smaller secondary fitness (one DSETP per pair).  rank' is the
+            // stable rank unless two children tie or one of the values is a NaN, and in both cases two children share a rank'
+            // (equal values count the same set; a NaN counts nobody, like the smallest value) - so the ranks the warp found are
+            // collected in a bitmap, and only if fewer distinct ranks than children turn up the exact pass (ties broken by child
+            // slot: lt | (eq & before)) runs.  Both passes give the reference's order; the exact one is the rare path.
             const int c0 = lane < 2 ? lane + 32 : lane;
-            auto rank_block = [&](auto nb_tag, int j0) {
+            auto rank_all = [&](auto nb_tag) {
                 constexpr int NB = decltype(nb_tag)::value;
                 double mine[NB];
                 int rank[NB];
 #pragma unroll
                 for(int j = 0; j < NB; j++)
                 {
-                    const int c = c0 + 32 * (j0 + j);
+                    const int c = c0 + 32 * j;
                     mine[j] = c < C ? s_sf[c] : 0.0;
                     rank[j] = 0;
                 }
@@ -889,17 +894,39 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 {
                     const double other = s_sf[o];
 #pragma unroll
+                    for(int j = 0; j < NB; j++) rank[j] += other < mine[j] ? 1 : 0;
+                }
+                // distinct ranks of the task: bit r of the bitmap = some child has rank' r (ranks are < C - 2 <= 32 * NB)
+                int distinct = 0;
+#pragma unroll
+                for(int w = 0; w < NB; w++)
+                {
+                    unsigned bits = 0u;
+#pragma unroll
                     for(int j = 0; j < NB; j++)
+                        if(c0 + 32 * j < C && (rank[j] >> 5) == w) bits |= 1u << (rank[j] & 31);
+                    distinct += __popc(__reduce_or_sync(gmask, bits));
+                }
+                if(distinct != C - 2) // warp-uniform
+                {
+#pragma unroll
+                    for(int j = 0; j < NB; j++) rank[j] = 0;
+                    for(int o = 2; o < C; o++)
                     {
-                        // no short-circuit: evaluated as predicate logic, not as data-dependent (divergent) branches
-                        const int lt = other < mine[j] ? 1 : 0, eq = other == mine[j] ? 1 : 0, before = o < c0 + 32 * (j0 + j) ? 1 : 0;
-                        rank[j] += lt | (eq & before);
+                        const double other = s_sf[o];
+#pragma unroll
+                        for(int j = 0; j < NB; j++)
+                        {
+                            // no short-circuit: evaluated as predicate logic, not as data-dependent (divergent) branches
+                            const int lt = other < mine[j] ? 1 : 0, eq = other == mine[j] ? 1 : 0, before = o < c0 + 32 * j ? 1 : 0;
+                            rank[j] += lt | (eq & before);
+                        }
                     }
                 }
 #pragma unroll
                 for(int j = 0; j < NB; j++)
                 {
-                    const int c = c0 + 32 * (j0 + j);
+                    const int c = c0 + 32 * j;
                     if(c >= C) continue;
                     if(2 + rank[j] >= child_count) continue;
                     uint64_t kk = fast_fitness_key(s_fit[c]);
@@ -915,14 +942,13 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                     }
                 }
             };
-            const int per_lane = (C - 2 + 31) / 32; // children of the busiest lane
+            const int per_lane = (C - 2 + 31) / 32; // children of the busiest lane (C <= 256: at most 8)
             if(per_lane <= 2)
-                rank_block(std::integral_constant<int, 2>{}, 0);
+                rank_all(std::integral_constant<int, 2>{});
+            else if(per_lane <= 4)
+                rank_all(std::integral_constant<int, 4>{});
             else
-            {
-#pragma unroll 1
-                for(int j0 = 0; j0 < per_lane; j0 += 4) rank_block(std::integral_constant<int, 4>{}, j0);
-            }
+                rank_all(std::integral_constant<int, 8>{});
         }
 
         // ---- selection (:410-431): two strict-< scans in position order ----------------------------------

@@ -24,29 +24,19 @@ namespace bioik
 // for every gene the goal applies to, in gene order.  term() is the loop body of goal_value's case, operation for operation.
 BIOIK_HD bool is_summing_joint_goal(int type) { return type == G_AVOID_JOINT_LIMITS || type == G_CENTER_JOINTS || type == G_REGULARIZATION || type == G_MINIMAL_DISPLACEMENT; }
 BIOIK_HD bool joint_term_applies(const DProblem& P, int type, int i) { return (type == G_AVOID_JOINT_LIMITS || type == G_CENTER_JOINTS) ? P.genes[i].clip_max != DBLMAX : true; }
-BIOIK_HD double joint_term(const DProblem& P, int type, int i, double x, const double* seed)
+// term() per goal type (x = the variable's value), with r = {centre, half span, weight, avoid} built once per task:
+//   AvoidJointLimitsGoal  d = x - (min + max) / 2;  d = max(0, |d| * 2 - span / 2);  d *= weight     goal_types.h:387-401
+//   CenterJointsGoal      d = x - (min + max) / 2;  d *= weight                                        goal_types.h:412-425
+//   RegularizationGoal    d = x - seed                                                                 goal_types.h:435-444
+//   MinimalDisplacement   d = x - seed;  d *= weight                                                   goal_types.h:455-465
+// and the term is d * d.  A lane asks for the term of ITS variable, so reading DProblem::genes[i] / seed[var] at that point would
+// be a lane-divergent constant-bank access plus a global load per call (the top stall of this kernel on cfg4 before the records).
+// RegularizationGoal has no weight factor: * 1.0 is exact.
+BIOIK_HD double joint_term_rec(const double* r, double x)
 {
-    const DGene& Gn = P.genes[i];
-    double d;
-    switch(type)
-    {
-    case G_AVOID_JOINT_LIMITS: // goal_types.h:387-401
-        d = x - (Gn.vmin + Gn.vmax) * 0.5;
-        d = BIOIK_FMAX(0.0, BIOIK_FABS(d) * 2.0 - Gn.span * 0.5);
-        d *= Gn.vel_weight;
-        break;
-    case G_CENTER_JOINTS: // goal_types.h:412-425
-        d = x - (Gn.vmin + Gn.vmax) * 0.5;
-        d *= Gn.vel_weight;
-        break;
-    case G_REGULARIZATION: // goal_types.h:435-444
-        d = x - seed[Gn.var];
-        break;
-    default: // G_MINIMAL_DISPLACEMENT, goal_types.h:455-465
-        d = x - seed[Gn.var];
-        d *= Gn.vel_weight;
-        break;
-    }
+    double d = x - r[0];
+    if(r[3] != 0.0) d = BIOIK_FMAX(0.0, BIOIK_FABS(d) * 2.0 - r[1]);
+    d *= r[2];
     return d * d;
 }
 
@@ -90,7 +80,8 @@ struct GroupLayout
     __host__ __device__ int o_sc() const { return o_gv() + 3 * G; }
     __host__ __device__ int o_carry() const { return o_sc() + 8; }               // [7T] reference-quirk mode: the frames left in phenotypes3
     __host__ __device__ int o_jt() const { return o_carry() + (stale ? 7 * T : 0); } // [3][NJ][n] terms of the summing joint-space goals, rows as gv
-    __host__ __device__ int o_int() const { return o_jt() + 3 * NJ * n; }
+    __host__ __device__ int o_jr() const { return o_jt() + 3 * NJ * n; }             // [NJ][n][4] records of joint_term_rec (rows as jt's slots)
+    __host__ __device__ int o_int() const { return o_jr() + 4 * NJ * n; }
     // int32: pair_start [T + 1], pair_gene [K], pair_of [T][n] (-1: the gene cannot move the tip), sum_slot [G] (row of jt, -1: not a
     // summing joint-space goal); reference-quirk mode: prev_pair [T][n] = pair of the last earlier gene that moves tip t (-1: none)
     __host__ __device__ int ints() const { return T + 1 + K + T * n + G + (stale ? T * n : 0); }
@@ -143,14 +134,14 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOI
     double* Wk = smem + (size_t)(warp_in_block * GPW + gw) * L.total();
     double *ind = Wk + L.o_ind(), *graw = Wk + L.o_graw(), *grad = Wk + L.o_grad(), *ta = Wk + L.o_ta(), *tb = Wk + L.o_tb(), *base = Wk + L.o_base(), *clip = Wk + L.o_clip();
     double *tip0 = Wk + L.o_tip0(), *f2 = Wk + L.o_f2(), *pl = Wk + L.o_pl(), *delta = Wk + L.o_delta(), *dxa = Wk + L.o_dxa(), *dxb = Wk + L.o_dxb();
-    double *gp = Wk + L.o_gp(), *gv = Wk + L.o_gv(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry(), *jt = Wk + L.o_jt();
+    double *gp = Wk + L.o_gp(), *gv = Wk + L.o_gv(), *sc = Wk + L.o_sc(), *carry = Wk + L.o_carry(), *jt = Wk + L.o_jt(), *jr = Wk + L.o_jr();
     int32_t* pair_start = (int32_t*)(Wk + L.o_int());
     int32_t *pair_gene = pair_start + T + 1, *pair_of = pair_gene + K, *sum_slot = pair_of + T * n, *prev_pair = sum_slot + G;
     const double* seed = S.seeds + (size_t)q * P.n_vars;
     // terms of the summing joint-space goals for gene i at value x -> row of jt
     auto store_terms = [&](int row, int i, double x) {
         for(int g = 0; g < G; g++)
-            if(sum_slot[g] >= 0) jt[((size_t)row * NJ + sum_slot[g]) * n + i] = joint_term(P, P.goals[g].type, i, x, seed);
+            if(sum_slot[g] >= 0) jt[((size_t)row * NJ + sum_slot[g]) * n + i] = joint_term_rec(jr + ((size_t)sum_slot[g] * n + i) * 4, x);
     };
 
     // the pair lists of the problem, next to the data they index
@@ -168,12 +159,29 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOI
     }
     __syncwarp();
     if(live)
+    {
         for(int k = gl; k < K; k += W)
         {
             int t = 0;
             while(pair_start[t + 1] <= k) t++;
             pair_of[t * n + pair_gene[k]] = k;
         }
+        for(int g = 0; g < G; g++)
+        {
+            if(sum_slot[g] < 0) continue;
+            const int type = P.goals[g].type;
+            for(int i = gl; i < n; i += W)
+            {
+                const DGene& Gn = P.genes[i];
+                const bool limits = type == G_AVOID_JOINT_LIMITS || type == G_CENTER_JOINTS;
+                double* r = jr + ((size_t)sum_slot[g] * n + i) * 4;
+                r[0] = limits ? (Gn.vmin + Gn.vmax) * 0.5 : seed[Gn.var];
+                r[1] = Gn.span * 0.5;
+                r[2] = type == G_REGULARIZATION ? 1.0 : Gn.vel_weight;
+                r[3] = type == G_AVOID_JOINT_LIMITS ? 1.0 : 0.0;
+            }
+        }
+    }
     __syncwarp();
     if(STALE && live)
     {
@@ -297,7 +305,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOI
                     {
                         // the stored terms of the current genes with this variable's term replaced
                         const double* t = jt + (size_t)sum_slot[g] * n;
-                        const double mine = joint_term(P, go.type, i, x.v, seed);
+                        const double mine = joint_term_rec(jr + ((size_t)sum_slot[g] * n + i) * 4, x.v);
                         double sum = 0.0;
                         for(int j = 0; j < n; j++)
                             if(joint_term_applies(P, go.type, j)) sum += j == i ? mine : t[j];

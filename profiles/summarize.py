@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns an ncu capture (gpurun_out/*.ncu-rep, brought back from the B200 box) into the small text summary that
 is committed under profiles/: launch configuration, time, pipe utilisation, DRAM traffic, stall reasons and the
-executed-instruction mix by opcode and by loop level.  Usage: python profiles/summarize.py <rep> <units> > out.txt
+executed-instruction mix by opcode and by loop level.  Usage: python profiles/summarize.py <rep | stem of exported csv pages> <units> > out.txt
 `units` = how many work units (warp-generations for k_evolve_fast, warps for k_serial) the capture covers."""
 import collections
 import csv
@@ -10,8 +10,13 @@ import subprocess
 import sys
 
 rep, units = sys.argv[1], float(sys.argv[2])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".ncu-rep"):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+else:  # <stem>: the two pages exported on the GPU box as <stem>.raw.csv and <stem>.source.csv.gz (the report itself embeds the whole library)
+    import gzip
+    raw = open(rep + ".raw.csv").read()
+    src = gzip.open(rep + ".source.csv.gz", "rt").read()
 rows = list(csv.reader(raw.splitlines()))
 hdr, unitrow, d = rows[0], rows[1], dict(zip(rows[0], rows[2]))
 print("kernel:", d.get("Kernel Name"))

@@ -68,6 +68,12 @@ static inline unsigned __reduce_min_sync(unsigned mask, unsigned v)
     }
     return m;
 }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    unsigned acc = v;
+    for(int o = __builtin_popcount(mask) / 2; o > 0; o >>= 1) acc |= sim_shfl(acc, (int)(threadIdx.x & 31) ^ o, mask);
+    return acc;
+}
 static inline unsigned __ballot_sync(unsigned mask, bool pred)
 {
     unsigned bit = pred ? (1u << (threadIdx.x & 31)) : 0u, acc = bit;
@@ -104,6 +110,7 @@ static inline void __threadfence() {}
 using std::max;
 using std::min;
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline double __longlong_as_double(long long v)
 {
     double r;

@@ -277,6 +277,20 @@ def test_mixed_goal_problem_on_gpu(oracle):
     gpu_util.assert_bit_equal(solver.trace(None, seeds, rs, 8), ref)
 
 
+@pytest.mark.parametrize("pop", [20, 128, 200])
+def test_preselection_with_tied_secondary_fitness_on_gpu(oracle, pop):
+    """AvoidJointLimitsGoal as the only secondary goal: most children score exactly 0.0, the pre-selection order (:366-378) is
+    decided by the child slot - the fast rank pass of the generation kernel has to fall back to its exact pass."""
+    w = workloads.cfg2(32)
+    pr = Problem().initialize(w.robot, w.group, [G.PoseGoal("r_wrist_roll_link"), G.AvoidJointLimitsGoal(1.0)])
+    w.problem = pr
+    w.generate(lambda rm, p, v: oracle.fk(rm, p, v), B=32, cfg_id=2)
+    cfg = oracle_lib.make_cfg(population=pop)
+    ref = oracle.solve(w.robot, pr, cfg, w.goal_params, w.seeds, w.rng_seeds, 6)
+    solver = IKSolver(w.robot, population=pop).initialize(pr)
+    gpu_util.assert_bit_equal(solver.trace(w.goal_params, w.seeds, w.rng_seeds, 6), ref)
+
+
 def test_mimic_joints_on_gpu(oracle):
     rm, groups = robots.mimic_gripper_arm()
     pr = Problem().initialize(rm, groups["all"], [G.PositionGoal("pad_a"), G.PoseGoal("pad_b")])

@@ -178,6 +178,23 @@ def test_mixed_goals_fast_kernel(sim, oracle):
             assert np.array_equal(a[k], b[k]), (k, fast)
 
 
+@pytest.mark.parametrize("pop", [20, 128, 200])
+def test_preselection_with_tied_secondary_fitness(sim, oracle, pop):
+    """AvoidJointLimitsGoal as the only secondary goal: most children score exactly 0.0, so the pre-selection order (:366-378)
+    is decided by the child slot - the generation kernel's fast rank pass must notice the ties and take its exact pass."""
+    from bio_ik_b200 import goals as G
+    w = workloads.cfg2(3)
+    pr = w.problem.__class__().initialize(w.robot, w.group, [G.PoseGoal("r_wrist_roll_link"), G.AvoidJointLimitsGoal(1.0)])
+    w.problem = pr
+    w.generate(lambda rm, p, v: oracle.fk(rm, p, v), B=3, cfg_id=2)
+    cfg = oracle_lib.make_cfg(population=pop)
+    a = oracle.solve(w.robot, pr, cfg, w.goal_params, w.seeds, w.rng_seeds, 3)
+    for fast in (False, True):
+        b = sim.solve(w.robot, pr, cfg, w.goal_params, w.seeds, w.rng_seeds, 3, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(a[k], b[k]), (k, fast)
+
+
 def test_mixed_goals_tip_major_kernel(sim, oracle):
     """Five tips (the tip-major generation kernel): link goals of several kinds with a tip read again later in the goal list, a
     secondary link goal (a setSecondary link goal sees the identity frames), primary and secondary joint-space goals."""
