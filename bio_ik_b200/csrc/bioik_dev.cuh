@@ -107,6 +107,7 @@ struct DGene // one active variable (problem.active_variables order)
     int32_t dep_start; // range in DProblem::dep_* (joint_dependencies of the variable's joint, :570-587)
     int32_t dep_count; // 0 if the variable's own joint mimics another joint (:623)
     int32_t tipmask;   // bit t set: the variable can move tip t (OR of its dependency joints' tipmask)
+    int32_t var_in_joint; // index of the variable inside its joint: the numeric Jacobian branch moves THIS variable of every dependency joint (:698-699)
     double clip_min, clip_max, span, vmin, vmax, vel_weight; // robot_info.h:48-55, problem.cpp:206-225
 };
 struct DGoal
@@ -420,7 +421,7 @@ template <class AV> BIOIK_HD F7 joint_frame_moved(const DSlot& S, AV vars, int w
     double v[7];
     const int cnt = S.type == J_PLANAR ? 3 : 7;
     for(int k = 0; k < cnt; k++) v[k] = vars[S.var + k];
-    v[which] = v[which] + dv;
+    if(which < cnt) v[which] = v[which] + dv; // a joint that mimics a joint with more variables: variables[ivar2] lies outside it, its frame does not move
     if(S.type == J_PLANAR) return planar_frame(v[0], v[1], v[2]);
     F7 f;
     f.p = V3{v[0], v[1], v[2]};
@@ -497,7 +498,8 @@ template <class AF, class AV> BIOIK_HD F7 delta_frame(const DProblem& P, AF fram
             // numeric differentiation (:695-726): move this variable by 1e-5, rebuild the link frame, carry the tip along
             // (change) and take the twist between the two tip frames (frameTwist, include/bio_ik/frame.h:240-259)
             const double step_size = 0.00001, inv_step_size = 1.0 / step_size;
-            const F7 jf2 = joint_frame_moved(S, vars, Gn.var - S.var, step_size);
+            // ivar2 (:698-699): the variable itself for its own joint, the same position inside a joint that mimics it
+            const F7 jf2 = joint_frame_moved(S, vars, Gn.var_in_joint, step_size);
             const F7 o = load_frame(S.origin);
             const F7 link2 = S.parent >= 0 ? concat(concat(load_frame(frames + 7 * S.parent), o), jf2) : concat(o, jf2);
             const F7 tip2 = frame_change(link2, lf, tipf);

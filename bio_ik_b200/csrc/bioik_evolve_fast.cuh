@@ -81,7 +81,12 @@ struct FastSmem
     __host__ __device__ int off_jq() const { return off_jrec() + (nj ? 4 * n : 0); }       // [MAXJ][n][4] joint-goal records: centre, half span, weight, on (nj > 0)
     __host__ __device__ int off_fit() const { return off_jq() + 4 * nj * n; } // [256] primary fitness per child slot
     __host__ __device__ int off_sf() const { return off_fit() + (lean ? 0 : 256); }   // [256] secondary fitness per child slot
-    __host__ __device__ int total() const { return ((off_sf() + (lean ? 0 : 256)) + 1) & ~1; }
+    // tip-major form: the warp-uniform operands of the chains in PAIR order, so that the chain loop walks them with pointer bumps
+    // instead of indexing by gene: [pairs][4] g0, base, clip_min, clip_max and [pairs][6] the gradient terms (the mutation-table
+    // offset gene * row of a pair sits in the pad slot 7 of its delta frame)
+    __host__ __device__ int off_prec() const { return off_sf() + (lean ? 0 : 256); }
+    __host__ __device__ int off_pterm() const { return off_prec() + 4 * pairs; }
+    __host__ __device__ int total() const { return ((off_pterm() + 6 * pairs) + 1) & ~1; }
 };
 
 // problems with three or more tips run the tip-major form of the generation kernel (select_evolve_fast)
@@ -400,6 +405,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     const int TT = TM ? P.T : T; // tips of the problem
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
     double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
+    double *s_prec = W + L.off_prec(), *s_pterm = W + L.off_pterm();
     const double* seed = S.seeds + (size_t)q * P.n_vars;
 
     // ---- stage the task -------------------------------------------------------------------
@@ -413,6 +419,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             while(P.tip_gene_start[t + 1] <= idx) t++;
             s_delta[idx * 8 + c7] = S.delta[(size_t)task * TT * n * 7 + ((size_t)t * n + P.tip_gene[idx]) * 7 + c7];
         }
+        for(int idx = lane; idx < L.pairs; idx += LPT) s_delta[idx * 8 + 7] = __longlong_as_double((long long)P.tip_gene[idx] * mtab_row(S.C));
     }
     else
         for(int k = lane; k < TT * n * 7; k += LPT)
@@ -441,6 +448,14 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     }
     for(int k = lane; k < G * GOAL_NPARAM; k += LPT) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
     __syncwarp(gmask);
+    if(TM) // the per-task part of the pair records: base and clip limits of the pair's gene
+        for(int idx = lane; idx < L.pairs; idx += LPT)
+        {
+            const int i = P.tip_gene[idx];
+            s_prec[4 * idx + 1] = s_rec[4 * i + 1];
+            s_prec[4 * idx + 2] = s_rec[4 * i + 2];
+            s_prec[4 * idx + 3] = s_rec[4 * i + 3];
+        }
     if(JOINT)
     {
         // One record per (joint-space goal, gene): every such goal adds ((x - centre) [-> max(0, |.| * 2 - half span)]) * weight,
@@ -527,6 +542,18 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             unclamped = LPT == 16 ? (safe & (safe >> 16)) : safe; // lanes 0..NG-1 of every lane group hold the genes
         }
         __syncwarp(gmask);
+        if(TM)
+        {
+            // the per-generation part of the pair records: parent gene and the six gradient terms of the pair's gene
+            for(int idx = lane; idx < L.pairs; idx += LPT)
+            {
+                const int i = P.tip_gene[idx];
+                s_prec[4 * idx + 0] = s_rec[4 * i + 0];
+#pragma unroll
+                for(int c = 0; c < 6; c++) s_pterm[6 * idx + c] = s_term[6 * i + c];
+            }
+            __syncwarp(gmask);
+        }
 
         // this lane's two best children so far: (key, packed = position * 512 + child)
         uint64_t k1 = FAST_KEY_NONE, k2 = FAST_KEY_NONE;
@@ -622,19 +649,29 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                                 for(int j = 0; j < 7; j++) F[k][0][j] = s_tip0[8 * t + j];
                             int idx = P.tip_gene_start[t];
                             const int i1 = P.tip_gene_start[t + 1];
-                            // mutation terms are fetched one list entry ahead of their use
-                            double m[CH];
-                            int i = idx < i1 ? P.tip_gene[idx] : 0;
+                            // the chain walks the pair records (s_prec, s_delta, s_pterm are in pair order): pointer bumps, no indexing by
+                            // gene; mutation terms are fetched one list entry ahead of their use, from the table offset in the pad slot
+                            // of the pair's delta frame
+                            const double* pr = s_prec + 4 * idx;
+                            const double* D = s_delta + 8 * idx;
+                            const double* pt[CH];
 #pragma unroll
-                            for(int k = 0; k < CH; k++) m[k] = BIOIK_LDG(mt + (size_t)i * R + jbase + LPT * k);
+                            for(int k = 0; k < CH; k++) pt[k] = s_pterm + 6 * idx + (tp[k] - s_term);
+                            const double* mb = mt + jbase;
+                            double m[CH];
+                            {
+                                const long long off = idx < i1 ? __double_as_longlong(D[7]) : 0ll;
+#pragma unroll
+                                for(int k = 0; k < CH; k++) m[k] = BIOIK_LDG(mb + off + LPT * k);
+                            }
+#pragma unroll 2
                             for(; idx < i1; idx++)
                             {
-                                const int inext = idx + 1 < i1 ? P.tip_gene[idx + 1] : i;
+                                const long long offn = __double_as_longlong(idx + 1 < i1 ? D[8 + 7] : D[7]);
                                 double mnext[CH];
 #pragma unroll
-                                for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mt + (size_t)inext * R + jbase + LPT * k);
-                                const double g0 = s_rec[4 * i + 0], base = s_rec[4 * i + 1], lo = s_rec[4 * i + 2], hi = s_rec[4 * i + 3];
-                                const double* D = s_delta + (size_t)idx * 8;
+                                for(int k = 0; k < CH; k++) mnext[k] = BIOIK_LDG(mb + offn + LPT * k);
+                                const double g0 = pr[0], base = pr[1], lo = pr[2], hi = pr[3];
                                 double Dv[7];
 #pragma unroll
                                 for(int j = 0; j < 7; j++) Dv[j] = D[j];
@@ -642,15 +679,17 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                                 for(int k = 0; k < CH; k++)
                                 {
                                     double gene = g0;
-                                    gene += m[k];          // gene += r * f      (:293)
-                                    gene += tp[k][6 * i];  // gene += gradient   (:296)
+                                    gene += m[k];     // gene += r * f      (:293)
+                                    gene += pt[k][0]; // gene += gradient   (:296)
                                     gene = clampd(gene, lo, hi);
                                     const double d = gene - base; // :1086
 #pragma unroll
                                     for(int j = 0; j < 7; j++) F[k][0][j] = BIOIK_FMA(d, Dv[j], F[k][0][j]);
                                     m[k] = mnext[k];
+                                    pt[k] += 6;
                                 }
-                                i = inext;
+                                pr += 4;
+                                D += 8;
                             }
                         }
 #pragma unroll

@@ -171,7 +171,6 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         DSlot& S = P.slots[s];
         S.parent = R.parent[l] >= 0 ? slot_of_link[R.parent[l]] : -1;
         S.type = R.jtype[l];
-        if((S.type == BIOIK_JOINT_FLOATING || S.type == BIOIK_JOINT_PLANAR) && R.mimic[l] >= 0) return host_fail(err, BIOIK_E_UNSUPPORTED_JOINT, "mimicking floating / planar joints are not supported");
         S.var = R.first_var[l];
         S.tipmask = 0;
         for(int k = 0; k < 7; k++) S.origin[k] = R.origin[7 * l + k];
@@ -226,6 +225,7 @@ inline int build_problem(const HostRobot& R, const BioikProblem* p, DProblem& P,
         P.gene_of_var[v] = i;
         DGene& Gn = P.genes[i];
         Gn.var = v;
+        Gn.var_in_joint = R.var_joint[v] >= 0 ? v - R.first_var[R.var_joint[v]] : 0;
         bool bounded = R.var_bounded[v] != 0;
         int j = R.var_joint[v];
         if(j >= 0 && R.jtype[j] == BIOIK_JOINT_REVOLUTE)

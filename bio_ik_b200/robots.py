@@ -220,6 +220,40 @@ def planar_base_arm():
     return rm, groups
 
 
+def mimic_virtual_joint_arm():
+    """An arm whose PLANAR joint mimics a prismatic joint and whose FLOATING joint mimics a revolute joint - and a revolute joint that
+    mimics the planar one's source again below them.  The reference resolves mimic for any joint type: updateMimic copies the FIRST
+    variable (src/forward_kinematics.h:230-246: the x translation of both virtual joints follows its source, their other variables
+    keep the seed values), and the Jacobian reaches such a joint through the numeric branch with the variable at the same position
+    inside the mimicking joint moved (ivar2, :698-699), scaled by the mimic factor (:624-630)."""
+    from ._abi import JOINT_FLOATING, JOINT_PLANAR
+    links = [
+        Link("base", None, JOINT_FIXED, joint_name="world_joint"),
+        Link("l1", "base", JOINT_REVOLUTE, xyz=(0, 0, 0.3), axis=(0, 0, 1), lower=-2.5, upper=2.5, velocity=2.0, joint_name="j1"),
+        Link("l2", "l1", JOINT_PRISMATIC, xyz=(0.1, 0, 0.2), rpy=(0.3, 0, 0), axis=(1, 0, 0), lower=-0.2, upper=0.3, velocity=0.5, joint_name="j2"),
+        Link("sled", "l2", JOINT_PLANAR, xyz=(0.05, 0.0, 0.1), rpy=(0.0, 0.1, 0.2), velocity=1.0, joint_name="sled_joint", mimic="j2", mimic_factor=0.7, mimic_offset=0.02,
+             var_lower=[-1.0, -1.0, -3.0], var_upper=[1.0, 1.0, 3.0], var_bounded=[1, 1, 1]),
+        Link("l3", "sled", JOINT_REVOLUTE, xyz=(0.3, 0, 0), axis=(0, 1, 0), lower=-2.2, upper=2.2, velocity=3.0, joint_name="j3"),
+        Link("pod", "l3", JOINT_FLOATING, xyz=(0.1, 0.0, 0.05), rpy=(0.1, 0.0, 0.0), velocity=1.0, joint_name="pod_joint", mimic="j3", mimic_factor=-0.25, mimic_offset=0.01,
+             var_lower=[-0.6, -0.6, -0.3, -1.0, -1.0, -1.0, -1.0], var_upper=[0.6, 0.6, 0.5, 1.0, 1.0, 1.0, 1.0], var_bounded=[1, 1, 1, 1, 1, 1, 1]),
+        Link("l4", "pod", JOINT_REVOLUTE, xyz=(0.2, 0, 0), axis=(0, 0, 1), lower=-1.5, upper=1.5, velocity=1.0, joint_name="j4", mimic="j2", mimic_factor=2.0, mimic_offset=-0.1),
+        Link("ee", "l4", JOINT_FIXED, xyz=(0.15, 0, 0), rpy=(0, 0.3, 0), joint_name="ee_joint"),
+        Link("probe", "sled", JOINT_FIXED, xyz=(0.0, 0.1, 0.2), joint_name="probe_joint"),
+    ]
+    rm = RobotModel("mimic_virtual_joint_arm", links)
+    groups = {"all": JointModelGroup(rm, "all", ["j1", "j2", "sled_joint", "j3", "pod_joint", "j4"], ["ee", "probe"])}
+    return rm, groups
+
+
+def mimic_virtual_joint_base(rm):
+    """a configuration of mimic_virtual_joint_arm whose non-mimicked virtual-joint variables (y, theta; y, z, quaternion) are set"""
+    base = np.zeros(rm.n_vars)
+    for name, v in (("sled_joint/y", 0.04), ("sled_joint/theta", 0.3), ("pod_joint/trans_y", -0.03), ("pod_joint/trans_z", 0.05),
+                    ("pod_joint/rot_x", 0.1), ("pod_joint/rot_y", -0.2), ("pod_joint/rot_z", 0.05), ("pod_joint/rot_w", 0.97)):
+        base[rm.variable_names.index(name)] = v
+    return base
+
+
 def balancing_tree(seed=5):
     """random_tree with URDF-style inertials on most links (mass, centre of mass in the link frame): the robot of the
     BalanceGoal tests.  12 of its 13 links carry mass, so the problem has 12+ tip links (every link with mass becomes one)."""

@@ -308,6 +308,26 @@ def test_mimic_joints_on_gpu(oracle):
     gpu_util.assert_bit_equal(solver.trace(gp, seeds, rs, 12), ref)
 
 
+def test_virtual_joints_that_mimic_on_gpu(oracle):
+    """a PLANAR joint mimicking a prismatic joint, a FLOATING joint mimicking a revolute one (forward_kinematics.h:230-246,698-699)"""
+    rm, groups = robots.mimic_virtual_joint_arm()
+    pr = Problem().initialize(rm, groups["all"], [G.PoseGoal("ee"), G.PositionGoal("probe")])
+    rng = np.random.default_rng(2)
+    B = 40
+    base = robots.mimic_virtual_joint_base(rm)
+    tg = workloads.sample_configurations(rm, pr.active_variables, B, rng, base=base)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng, base=base)
+    tips = oracle.fk(rm, pr, tg)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    gp[:, 0, 0:7], gp[:, 1, 0:3] = tips[:, 0, :], tips[:, 1, 0:3]
+    cfg = oracle_lib.make_cfg(population=64)
+    rs = np.arange(B, dtype=np.uint32) + 1
+    ref = oracle.solve(rm, pr, cfg, gp, seeds, rs, 10)
+    solver = IKSolver(rm, population=64).initialize(pr)
+    assert np.array_equal(solver.fk(seeds), oracle.fk(rm, pr, seeds))
+    gpu_util.assert_bit_equal(solver.trace(gp, seeds, rs, 10), ref)
+
+
 # ---------------------------------------------------------------------------------------------
 # SURVEY.md §8(f) rows 1 and 3: islands of one query, IKParallel's selection, the plugin's angle wrap
 # ---------------------------------------------------------------------------------------------

@@ -255,6 +255,36 @@ def test_mimic_joints(sim, oracle):
             assert np.array_equal(a[k], b[k]), (k, fast)
 
 
+def test_virtual_joints_that_mimic(sim, oracle):
+    """a PLANAR joint mimicking a prismatic joint, a FLOATING joint mimicking a revolute one (first variable only, forward_kinematics.h:
+    230-246) and the numeric Jacobian branch reached through the mimic dependency (ivar2, :698-699)"""
+    from bio_ik_b200 import goals as G, robots
+    from bio_ik_b200.problem import Problem
+    rm, groups = robots.mimic_virtual_joint_arm()
+    pr = Problem().initialize(rm, groups["all"], [G.PoseGoal("ee"), G.PositionGoal("probe")])
+    assert [rm.variable_names[i] for i in pr.active_variables] == ["j1", "j2", "j3"]
+    rng = np.random.default_rng(2)
+    base = robots.mimic_virtual_joint_base(rm)
+    tg = workloads.sample_configurations(rm, pr.active_variables, 3, rng, base=base)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, 3, rng, base=base)
+    tips = oracle.fk(rm, pr, tg)
+    gp = np.repeat(pr.default_goal_params()[None], 3, 0)
+    gp[:, 0, 0:7], gp[:, 1, 0:3] = tips[:, 0, :], tips[:, 1, 0:3]
+    tips_s, delta_s = sim.fk(rm, pr, seeds, delta=True)
+    assert np.array_equal(tips_s, oracle.fk(rm, pr, seeds))
+    d, mask = oracle.approx(rm, pr, seeds)
+    d = d.copy()
+    d[mask == 0, 6] = 0.0  # device convention: unmasked delta frames are all-zero
+    assert np.array_equal(delta_s, d) and np.all(mask[:, 0, :] == 1)  # every gene moves the end effector, two of them through a mimicking virtual joint
+    cfg = oracle_lib.make_cfg(population=40)
+    rs = np.arange(3, dtype=np.uint32) + 1
+    a = oracle.solve(rm, pr, cfg, gp, seeds, rs, 5)
+    for fast in (0, 1):
+        b = sim.solve(rm, pr, cfg, gp, seeds, rs, 5, fast=fast)
+        for k in ("genes", "gradients", "species_fitness", "solutions", "fitness"):
+            assert np.array_equal(a[k], b[k]), (k, fast)
+
+
 @pytest.mark.parametrize("B,pop,mode,steps,early", [(5, 128, "q", 5, False), (19, 64, "q", 3, False), (33, 128, "l", 2, False), (18, 128, "q", 9, True), (3, 200, 0, 3, False)])
 def test_persistent_kernel_is_bit_identical_to_the_oracle(sim, oracle, B, pop, mode, steps, early):
     """bioik_persist.cuh: the whole solve as work items (evolve(query, step), serial(group of 16 queries, step)) taken from two

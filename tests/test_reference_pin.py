@@ -236,6 +236,26 @@ def test_mimic_joints_and_prismatic(ref, oracle):
         compare(oracle, ref, rm, pr, cfg, gp, seeds, 11 + np.arange(B, dtype=np.uint32), 6)
 
 
+def test_virtual_joints_that_mimic(ref, oracle):
+    """a PLANAR joint mimicking a prismatic joint and a FLOATING joint mimicking a revolute one in the reference's code: updateMimic
+    copies the first variable (forward_kinematics.h:230-246), the Jacobian reaches them through the numeric branch with ivar2 (:698-699)"""
+    rm, groups = robots.mimic_virtual_joint_arm()
+    g = groups["all"]
+    pr = Problem().initialize(rm, g, [G.PoseGoal("ee"), G.PositionGoal("probe")])
+    rng = np.random.default_rng(8)
+    B = 12
+    base = robots.mimic_virtual_joint_base(rm)
+    targets = workloads.sample_configurations(rm, pr.active_variables, B, rng, base=base)
+    seeds = workloads.sample_configurations(rm, pr.active_variables, B, rng, base=base)
+    tips = oracle.fk(rm, pr, targets, libm=True)
+    gp = np.repeat(pr.default_goal_params()[None], B, 0)
+    gp[:, 0, 0:7], gp[:, 1, 0:3] = tips[:, 0, :], tips[:, 1, 0:3]
+    for mode in ("bio2_memetic", "bio2_memetic_l", "bio2"):
+        memetic, gens = MODES[mode]
+        cfg = oracle_lib.make_cfg(population=18, memetic=memetic, generations=gens)
+        compare(oracle, ref, rm, pr, cfg, gp, seeds, 11 + np.arange(B, dtype=np.uint32), 6)
+
+
 @pytest.mark.parametrize("maker", ["floating_base_arm", "planar_base_arm"])
 @pytest.mark.parametrize("group", ["whole_arm", "all"])
 def test_floating_and_planar_joints(ref, oracle, group, maker):
