@@ -238,16 +238,34 @@ BIOIK_HD void joint_goal_accumulate(int type, int var_index, int i, double x, do
     }
 }
 
-// warp argmin of (fitness key, packed position/child) with three REDUX.MIN: ties -> lowest position (:419-423)
 // (over the lanes of `mask`: the whole warp, or the aligned lane group of one task)
-__device__ __forceinline__ uint32_t fast_warp_argmin(uint64_t key, uint32_t packed, unsigned mask = 0xffffffffu)
+// min over the LPT lanes of a task.  With 16 lanes per task the two groups of a warp run the two species of ONE query: they enter,
+// loop and leave together, so the reduction is issued warp-wide with a constant full mask - one REDUX per group, back to back.
+// (A group mask known only at run time makes the compiler wrap every warp primitive in mask-matching code and run the groups one
+// after the other: 12 % of the single-pose kernel's time before this form.)
+template <int LPT> __device__ __forceinline__ uint32_t group_reduce_min(uint32_t v, unsigned gmask, int lane0)
+{
+    if(LPT == 32) return __reduce_min_sync(0xffffffffu, v);
+    if(LPT == 16)
+    {
+        const bool upper = lane0 != 0;
+        const uint32_t a = __reduce_min_sync(0xffffffffu, upper ? 0xFFFFFFFFu : v);
+        const uint32_t b = __reduce_min_sync(0xffffffffu, upper ? v : 0xFFFFFFFFu);
+        return upper ? b : a;
+    }
+    return __reduce_min_sync(gmask, v);
+}
+// argmin of (fitness key, packed position/child) over the lanes of a task with three reductions: ties -> lowest position (:419-423);
+// wkey = the winning key, i.e. the winner's fitness bits
+template <int LPT> __device__ __forceinline__ uint32_t fast_warp_argmin(uint64_t key, uint32_t packed, unsigned gmask, int lane0, uint64_t& wkey)
 {
     uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-    uint32_t mh = __reduce_min_sync(mask, hi);
+    uint32_t mh = group_reduce_min<LPT>(hi, gmask, lane0);
     uint32_t l2 = (hi == mh) ? lo : 0xFFFFFFFFu;
-    uint32_t ml = __reduce_min_sync(mask, l2);
+    uint32_t ml = group_reduce_min<LPT>(l2, gmask, lane0);
     uint32_t p2 = (hi == mh && lo == ml) ? packed : 0xFFFFFFFFu;
-    return __reduce_min_sync(mask, p2);
+    wkey = ((uint64_t)mh << 32) | (uint64_t)ml;
+    return group_reduce_min<LPT>(p2, gmask, lane0);
 }
 __device__ __forceinline__ uint64_t fast_fitness_key(double f) { return (f != f) ? 0xFFFFFFFFFFFFFFFEull : (uint64_t)__double_as_longlong(f); }
 constexpr uint64_t FAST_KEY_NONE = 0xFFFFFFFFFFFFFFFFull;
@@ -380,6 +398,9 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     // the single-pose problem with a compile-time gene count (NG <= 8 genes sit in the first lanes of a lane group; with 16 lanes per
     // task both groups of a warp hold the two species of one query, so they enter and leave together and warp-wide votes are safe)
     constexpr bool LEAN = NG != 0 && NG <= 8 && GSPEC == 1 && !JOINT && !TM && (LPT == 16 || LPT == 32);
+    // mask of the warp-level primitives: with 16 lanes per task both groups of the warp are always here together (above), so they
+    // are issued warp-wide with a constant mask; lane indices passed to shuffles are warp lanes (lane0 + ...) either way
+    const unsigned smask = (LPT == 32 || LPT == 16) ? 0xffffffffu : gmask;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
     if(run_done(S, q, step)) return;
@@ -447,7 +468,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         }
     }
     for(int k = lane; k < G * GOAL_NPARAM; k += LPT) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
-    __syncwarp(gmask);
+    __syncwarp(smask);
     if(TM) // the per-task part of the pair records: base and clip limits of the pair's gene
         for(int idx = lane; idx < L.pairs; idx += LPT)
         {
@@ -484,7 +505,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             }
             j++;
         }
-        __syncwarp(gmask);
+        __syncwarp(smask);
     }
 
     // Fitness of the two parents under this step's approximator.  Within a step the parents of generation
@@ -492,7 +513,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     // so children[0..1] (:381-388,:401-407) are evaluated once here and carried in registers afterwards.
     double pf = 0.0;
     if(lane < 2) pf = TM ? fast_eval_one_tips<JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed) : fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
-    double f_par0 = __shfl_sync(gmask, pf, lane0 + 0), f_par1 = __shfl_sync(gmask, pf, lane0 + 1);
+    double f_par0 = __shfl_sync(smask, pf, lane0 + 0), f_par1 = __shfl_sync(smask, pf, lane0 + 1);
 
     int cur = 0;                 // parent buffer in use
     const int parity = lane & 1; // child slot c = j + 2 is even <=> lane is even
@@ -541,7 +562,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             const unsigned safe = __ballot_sync(0xffffffffu, gene_safe);
             unclamped = LPT == 16 ? (safe & (safe >> 16)) : safe; // lanes 0..NG-1 of every lane group hold the genes
         }
-        __syncwarp(gmask);
+        __syncwarp(smask);
         if(TM)
         {
             // the per-generation part of the pair records: parent gene and the six gradient terms of the pair's gene
@@ -552,7 +573,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
 #pragma unroll
                 for(int c = 0; c < 6; c++) s_pterm[6 * idx + c] = s_term[6 * i + c];
             }
-            __syncwarp(gmask);
+            __syncwarp(smask);
         }
 
         // this lane's two best children so far: (key, packed = position * 512 + child)
@@ -909,7 +930,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         {
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
-            __syncwarp(gmask);
+            __syncwarp(smask);
             // the lane's children c0, c0 + 32, ... (c0 = its first child slot >= 2), all NB of them together: one broadcast read of
             // every other child's secondary fitness serves NB ranks.
             // Fast pass: rank' = how many children have a strictly smaller secondary fitness (one DSETP per pair).  rank' is the
@@ -993,13 +1014,14 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         // ---- selection (:410-431): two strict-< scans in position order ----------------------------------
         // candidates: parent 0 at position 0, parent 1 at position 1 (cached fitness), each lane's best child
         uint32_t w1;
+        uint64_t wkey1, wkey2; // keys of the two winners = their fitness bits
         {
             uint64_t kk = k1;
             uint32_t pk = q1;
             uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
             if(lane == 0 && key_less(kp0, 0u, kk, pk)) { kk = kp0; pk = 0u; }
             if(lane == 1 && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
-            w1 = fast_warp_argmin(kk, pk, gmask);
+            w1 = fast_warp_argmin<LPT>(kk, pk, gmask, lane0, wkey1);
             if(f_par0 != f_par0) w1 = 0u; // position 0 holds a NaN: `f < fmin` never fires (:418-422)
         }
         const uint32_t w1_pos = w1 >> 9, w1_child = w1 & 511u;
@@ -1012,7 +1034,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
             uint64_t kp0 = fast_fitness_key(f_par0), kp1 = fast_fitness_key(f_par1);
             if(lane == 0 && w1_child != 0u && key_less(kp0, w1_pos * 512u, kk, pk)) { kk = kp0; pk = w1_pos * 512u; }
             if(lane == 1 && w1_child != 1u && key_less(kp1, 512u + 1u, kk, pk)) { kk = kp1; pk = 512u + 1u; }
-            w2 = fast_warp_argmin(kk, pk, gmask);
+            w2 = fast_warp_argmin<LPT>(kk, pk, gmask, lane0, wkey2);
             // the scan starts at position 1: its occupant wins if its fitness is NaN
             uint32_t occ1 = (w1_pos == 1u) ? 0u : 1u;
             double f_occ1 = occ1 == 0u ? f_par0 : f_par1;
@@ -1020,24 +1042,11 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         }
         const uint32_t w2_child = w2 & 511u;
 
-        // fitness of the winners = parents' fitness of the next generation
+        // fitness of the winners = parents' fitness of the next generation: a child's is the key its argmin returned (the key of a
+        // number is its bit pattern; a NaN comes back as a NaN), parents keep their cached value
         {
-            uint64_t kw1 = (k1 != FAST_KEY_NONE && q1 == w1) ? k1 : 0ull;
-            uint64_t kw2 = (k1 != FAST_KEY_NONE && q1 == w2) ? k1 : ((k2 != FAST_KEY_NONE && q2 == w2) ? k2 : 0ull);
-            // exactly one lane holds each child winner; parents keep their cached value
-            uint32_t own1 = __ballot_sync(gmask, w1_child >= 2u && q1 == w1);
-            uint32_t own2 = __ballot_sync(gmask, w2_child >= 2u && (q1 == w2 || q2 == w2));
-            double nf0 = w1_child == 0u ? f_par0 : f_par1, nf1 = w2_child == 0u ? f_par0 : f_par1;
-            if(own1)
-            {
-                uint64_t kb = __shfl_sync(gmask, kw1, __ffs(own1) - 1);
-                nf0 = __longlong_as_double((long long)kb);
-            }
-            if(own2)
-            {
-                uint64_t kb = __shfl_sync(gmask, kw2, __ffs(own2) - 1);
-                nf1 = __longlong_as_double((long long)kb);
-            }
+            const double nf0 = w1_child >= 2u ? __longlong_as_double((long long)wkey1) : (w1_child == 0u ? f_par0 : f_par1);
+            const double nf1 = w2_child >= 2u ? __longlong_as_double((long long)wkey2) : (w2_child == 0u ? f_par0 : f_par1);
             f_par0 = nf0;
             f_par1 = nf1;
         }
@@ -1073,7 +1082,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 }
             }
         }
-        __syncwarp(gmask);
+        __syncwarp(smask);
         cur ^= 1;
     }
 
