@@ -42,6 +42,7 @@ struct RunPlan
     int Q = 0, islands = 0; // bioik_begin: queries x islands (0: plain batch)
     EvolveFastKernel fast = nullptr;
     int evolve_lpt = 32; // lanes per task of the generation kernel
+    int evolve_wpb = BIOIK_EVOLVE_WPB; // warps per block of the generation kernel
     size_t evolve_smem = 0;
     MemeticGroupKernel mgk = nullptr;
     int mg_width = 8, mg_warps = 4;
@@ -411,7 +412,8 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     ctx->generic_now = ctx->force_generic || P.T > 8 || P.n_balance > 0;
     R.fast = ctx->generic_now ? nullptr : select_evolve_fast(P, S.C, ctx->ch_cap, &R.evolve_lpt, ctx->lpt_want);
     R.dominant = R.fast ? selected_kernel_name() : "k_evolve";
-    const int warps_per_block = BIOIK_EVOLVE_WPB;
+    const int warps_per_block = R.fast ? evolve_warps_per_block(R.evolve_lpt) : BIOIK_EVOLVE_WPB;
+    R.evolve_wpb = warps_per_block;
     if(R.fast)
     {
         FastSmem L = fast_smem_layout(P);
@@ -531,7 +533,7 @@ int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
     S.gauss_off = ctx->d_gauss_off;
     S.rate_exp = ctx->d_rate_exp;
     const DProblem& P = ctx->hP;
-    const int B = S.B, TPB = 128, warps_per_block = BIOIK_EVOLVE_WPB;
+    const int B = S.B, TPB = 128, warps_per_block = R.evolve_wpb;
     const int qblocks = (B + TPB - 1) / TPB, tblocks = (2 * B + TPB - 1) / TPB;
     if(!ctx->generic_now && R.persist)
     {

@@ -1096,7 +1096,23 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     }
 }
 
-template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int LPT = 32> __global__ void __launch_bounds__(32 * BIOIK_EVOLVE_WPB, (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
+// Launch bounds = the register budget.  The 16-lane single-pose kernels run best at THREE warps per scheduler with 168 registers
+// (no hot-loop spills: 250 us per cfg2 launch; 16 warps per SM at 128 registers with 136 B of spills: 285 us; 14 / 13 / 11 / 10 / 8 warps:
+// 273 / 260 / 293 / 283 / 283 us - profiles/r02_experiments.md §4) in blocks of two warps (finer block granularity in the last wave);
+// the other forms keep four warps per block and the occupancy they were tuned at.
+#ifndef BIOIK_EVOLVE_WPB16
+#define BIOIK_EVOLVE_WPB16 2 // warps per block of the 16-lane kernels
+#endif
+#ifndef BIOIK_EVOLVE_MINBLOCKS16
+#define BIOIK_EVOLVE_MINBLOCKS16 6
+#endif
+__host__ __device__ constexpr int evolve_warps_per_block(int lpt) { return lpt == 16 ? BIOIK_EVOLVE_WPB16 : BIOIK_EVOLVE_WPB; }
+#ifdef BIOIK_X_MAXNREG // experiment builds: an explicit register cap instead of a resident-block target
+#define BIOIK_EVOLVE_BOUNDS(T, CH, LPT) __maxnreg__(BIOIK_X_MAXNREG)
+#else
+#define BIOIK_EVOLVE_BOUNDS(T, CH, LPT) __launch_bounds__(32 * evolve_warps_per_block(LPT), (LPT == 16 ? BIOIK_EVOLVE_MINBLOCKS16 : (T * CH <= 4 ? BIOIK_EVOLVE_MINBLOCKS : (T * CH <= 6 ? 3 : 2))))
+#endif
+template <int T, int CH, int GSPEC, bool JOINT, int NG = 0, bool TM = false, int LPT = 32> __global__ void BIOIK_EVOLVE_BOUNDS(T, CH, LPT) k_evolve_fast(const DProblem* __restrict__ Pp, DState S, int step, const double* __restrict__ mtab)
 {
     extern __shared__ double smem[];
     const DProblem& P = *Pp;
