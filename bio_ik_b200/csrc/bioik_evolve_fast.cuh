@@ -26,6 +26,11 @@
 #define BIOIK_LDG(p) __ldg(p)
 #endif
 
+// 1: the single-pose kernels request the first mutation-table row of a chunk one chunk ahead (evolve_fast_task, EARLY)
+#ifndef BIOIK_EVOLVE_EARLYROW
+#define BIOIK_EVOLVE_EARLYROW 0
+#endif
+
 namespace bioik
 {
 
@@ -517,6 +522,16 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
 
     int cur = 0;                 // parent buffer in use
     const int parity = lane & 1; // child slot c = j + 2 is even <=> lane is even
+    // EARLY: the first mutation-table row of a chunk is requested while the previous chunk's fitness (or the previous generation's
+    // selection) is still being worked on, so its latency is off the chunk's dependent chain
+    constexpr bool EARLY = BIOIK_EVOLVE_EARLYROW && LEAN;
+    double m_early[EARLY ? CH : 1];
+    if(EARLY)
+    {
+        const double* mt0 = mtab + (size_t)((step * 2 + slot) * S.gens) * n * R;
+#pragma unroll
+        for(int k = 0; k < CH; k++) m_early[k] = BIOIK_LDG(mt0 + lane + LPT * k);
+    }
     const double wsq0 = P.goals[0].weight_sq;
 
     for(int gen = 0; gen < S.gens; gen++)
@@ -736,7 +751,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 // (two register buffers used alternately: no register rotation in the loop)
                 double mA[CH], mB[CH];
     #pragma unroll
-                for(int k = 0; k < CH; k++) mA[k] = BIOIK_LDG(mp + LPT * k);
+                for(int k = 0; k < CH; k++) mA[k] = EARLY ? m_early[k] : BIOIK_LDG(mp + LPT * k);
 
                 // one gene of all CH children; FIRST = the accumulators start from the base tip frames (no copy)
                 auto gene_step = [&](auto first_tag, int i, const double (&m)[CH], double (&mnext)[CH]) {
@@ -820,6 +835,18 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                         gene_step(std::false_type{}, i + 1, mA, mB);
                     }
                     if(i < n) gene_step(std::false_type{}, i, mB, mA);
+                }
+                if(EARLY)
+                {
+                    // next chunk of this generation, else the first chunk of the next generation (the table rows of the call after
+                    // the last one of the step exist: the schedule is sized for the whole solve; beyond it the request is skipped)
+                    const bool more = chunk + 1 < nchunks;
+                    const double* nx = more ? mt + jbase + LPT * CH : mt + (size_t)n * R + lane;
+                    if(more || gen + 1 < S.gens)
+                    {
+#pragma unroll
+                        for(int k = 0; k < CH; k++) m_early[k] = BIOIK_LDG(nx + LPT * k);
+                    }
                 }
             }
 
