@@ -39,7 +39,7 @@ template <int memetic> struct IKEvolution2B200 : IKBase
     };
     RobotTable table;
     bioik_ctx* ctx = nullptr;
-    int islands = 64, device = 0;
+    int islands = 64, device = 0, stream_stride = 0;
 
     // what bioik_set_problem was last called with: a new query with the same structure only needs bioik_begin
     std::vector<int32_t> set_tips, set_active;
@@ -119,6 +119,8 @@ template <int memetic> struct IKEvolution2B200 : IKBase
         cfg.table_seed = (uint32_t)params.random_seed, cfg.device = device;
         ctx = nullptr;
         if(bioik_create(&r, &cfg, &ctx) != BIOIK_OK) ERROR("bioik_create", bioik_last_error(nullptr));
+        // 0 (default): the islands are clones of one random stream like IKParallel's threads; k > 0: island i starts i * k steps into it
+        if(stream_stride > 0 && bioik_set_option(ctx, BIOIK_OPT_ISLAND_STREAM_STRIDE, stream_stride) != BIOIK_OK) ERROR("bioik_set_option", bioik_last_error(ctx));
         set_tips.clear(), set_active.clear(), set_goals.clear();
     }
 
@@ -127,6 +129,7 @@ template <int memetic> struct IKEvolution2B200 : IKBase
     {
         islands = envInt("BIOIK_B200_ISLANDS", 64);
         device = envInt("BIOIK_B200_DEVICE", 0);
+        stream_stride = envInt("BIOIK_B200_ISLAND_STREAM_STRIDE", 0);
         flattenRobot(*p.robot_model);
         createContext();
     }
@@ -136,6 +139,7 @@ template <int memetic> struct IKEvolution2B200 : IKBase
         , table(o.table)
         , islands(o.islands)
         , device(o.device)
+        , stream_stride(o.stream_stride)
     {
         createContext();
     }

@@ -16,6 +16,7 @@ OK, E_INVALID, E_UNSUPPORTED_GOAL, E_UNSUPPORTED_JOINT, E_CUDA, E_NO_PROBLEM, E_
 # joint types (moveit::core::JointModel::JointType subset, src/forward_kinematics.h:78-139)
 JOINT_FIXED, JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_FLOATING, JOINT_PLANAR = range(5)
 OPT_REFERENCE_STALE_TIPS = 1
+OPT_ISLAND_STREAM_STRIDE = 2  # islands of a query start i * value solver steps into the shared random streams (0: clones, as in the reference)
 JOINT_VARS = {JOINT_FIXED: 0, JOINT_REVOLUTE: 1, JOINT_PRISMATIC: 1, JOINT_FLOATING: 7, JOINT_PLANAR: 3}
 
 # goal types (include/bio_ik/goal_types.h)

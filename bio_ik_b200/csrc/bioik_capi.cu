@@ -107,6 +107,7 @@ struct bioik_ctx
     double ms_evolve = 0, ms_serial = 0;
     int64_t n_evolve = 0, n_serial = 0;
     bool stale_tips = false; // BIOIK_OPT_REFERENCE_STALE_TIPS
+    int island_stride = 0;   // BIOIK_OPT_ISLAND_STREAM_STRIDE
     int memetic_group = -1; // BIOIK_MEMETIC_GROUP: 0 = memetic step inside the thread-per-task serial kernel, 1 = always k_memetic_group, unset = by problem shape
     // query-level buffers of bioik_solve_islands
     double *d_q_gp = nullptr, *d_q_seeds = nullptr, *d_q_sol = nullptr, *d_q_fit = nullptr;
@@ -374,7 +375,9 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     ctx->run.open = false;
     if(ctx->pending.size() > 4096) drain_events(ctx); // bound the timing-event backlog
     if((rc = ensure_state(ctx, B)) != BIOIK_OK) return rc;
-    if((rc = ensure_schedules(ctx, std::max(std::min(total_steps, 64), 1))) != BIOIK_OK) return rc;
+    // islands reading the random streams ahead of island 0 need that much more of the schedules
+    const int stream_lead = islands > 1 ? (islands - 1) * ctx->island_stride : 0;
+    if((rc = ensure_schedules(ctx, std::max(std::min(total_steps, 64), 1) + stream_lead)) != BIOIK_OK) return rc;
     const DProblem& P = ctx->hP;
     DState& S = ctx->S;
     S.B = B;
@@ -385,6 +388,7 @@ int solve_begin(bioik_ctx* ctx, cudaStream_t st, int B, const double* d_gp, cons
     S.total_steps = total_steps;
     S.early_exit = early_exit;
     S.islands = islands;
+    S.island_stride = islands > 1 ? ctx->island_stride : 0;
     S.cancel = ctx->d_cancel;
     if(!d_gp)
     {
@@ -528,7 +532,7 @@ int solve_steps(bioik_ctx* ctx, cudaStream_t st, int s0, int s1, bool last)
     if(!R.open) return fail(ctx, BIOIK_E_INVALID, "no solve in progress (bioik_begin)");
     if(s1 <= s0) return BIOIK_OK;
     int rc;
-    if((rc = ensure_schedules(ctx, s1)) != BIOIK_OK) return rc;
+    if((rc = ensure_schedules(ctx, s1 + (ctx->S.islands > 1 ? (ctx->S.islands - 1) * ctx->S.island_stride : 0))) != BIOIK_OK) return rc;
     DState& S = ctx->S;
     S.gauss_off = ctx->d_gauss_off;
     S.rate_exp = ctx->d_rate_exp;
@@ -924,6 +928,11 @@ int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value)
     {
     case BIOIK_OPT_REFERENCE_STALE_TIPS:
         ctx->stale_tips = value != 0;
+        drop_graph(ctx);
+        return BIOIK_OK;
+    case BIOIK_OPT_ISLAND_STREAM_STRIDE:
+        if(value < 0 || value > 64) return fail(ctx, BIOIK_E_INVALID, "BIOIK_OPT_ISLAND_STREAM_STRIDE must be in [0, 64]");
+        ctx->island_stride = value;
         drop_graph(ctx);
         return BIOIK_OK;
     default: return fail(ctx, BIOIK_E_INVALID, "unknown option");

@@ -528,7 +528,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     double m_early[EARLY ? CH : 1];
     if(EARLY)
     {
-        const double* mt0 = mtab + (size_t)((step * 2 + slot) * S.gens) * n * R;
+        const double* mt0 = mtab + (size_t)((stream_step(S, q, step) * 2 + slot) * S.gens) * n * R;
 #pragma unroll
         for(int k = 0; k < CH; k++) m_early[k] = BIOIK_LDG(mt0 + lane + LPT * k);
     }
@@ -536,7 +536,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
 
     for(int gen = 0; gen < S.gens; gen++)
     {
-        const int call = (step * 2 + slot) * S.gens + gen;
+        const int call = (stream_step(S, q, step) * 2 + slot) * S.gens + gen;
         const double* mt = mtab + (size_t)call * n * R;
         const int child_count = P.has_secondary ? S.ccount[((size_t)q * 2 + slot) * S.gens + gen] : C;
         double* par = s_par + cur * 4 * n;

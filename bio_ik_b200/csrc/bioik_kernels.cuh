@@ -21,6 +21,7 @@ namespace bioik
 struct DState
 {
     int32_t B, C, gens, memetic, memetic_iters, total_steps, early_exit, islands; // islands > 1: run q is island q % islands of query q / islands
+    int32_t island_stride; // islands > 1: island k reads the query-independent random streams `k * island_stride` steps ahead (0: all islands share them)
     // inputs
     const double* goal_params; // [B][G][NPARAM]
     const double* seeds;       // [B][n_vars]
@@ -63,6 +64,11 @@ __device__ __forceinline__ void note_success(const DState& S, int q, int steps_d
     S.done[q] = 1;
     if(S.early_exit == 2 && S.islands > 1) atomicMin(&S.qstep[q / S.islands], steps_done);
 }
+
+// The step whose slice of the query-independent random streams (mutation table / gaussian slabs, rate exponents, fast_random values)
+// run q consumes at solver step `step`.  The reference's islands are clones that replay ONE stream; with
+// BIOIK_OPT_ISLAND_STREAM_STRIDE island k starts k * stride steps into it, so the islands of a query diverge from their first generation.
+__device__ __forceinline__ int stream_step(const DState& S, int q, int step) { return (S.islands > 1 && S.island_stride > 0) ? step + (q % S.islands) * S.island_stride : step; }
 
 constexpr uint32_t RANDOM_BUFFER_MASK = (1u << 23) - 1;
 constexpr uint32_t UNIFORM_INDEX0 = 6165936u; // XORShift64 output #1 & mask (src/ik_base.h:122)
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(128) k_evolve(const DProblem* __restrict__ Pp,
 
     for(int gen = 0; gen < S.gens; gen++)
     {
-        const int call = (step * 2 + slot) * S.gens + gen;
+        const int call = (stream_step(S, q, step) * 2 + slot) * S.gens + gen;
         const double* rr_base = S.gauss + S.gauss_off[call];
         const uint8_t* rexp = S.rate_exp + (size_t)call * (C - 2);
         const int child_count = P.has_secondary ? S.ccount[((size_t)q * 2 + slot) * S.gens + gen] : C;
@@ -389,7 +395,7 @@ __global__ void k_memetic(const DProblem* __restrict__ Pp, DState S, int step)
     for(int i = 0; i < n; i++) ind[i] = genes[i];
 
     double dp = 0.0000001; // :450
-    if(fast_random_at(S, step, slot) < 0.5) dp = -dp; // :451
+    if(fast_random_at(S, stream_step(S, q, step), slot) < 0.5) dp = -dp; // :451
     bool changed = false;
     for(int generation = 0; generation < S.memetic_iters; generation++)
     {
@@ -501,7 +507,7 @@ __global__ void k_species(const DProblem* __restrict__ Pp, DState S, int step)
     S.impr[q * 2 + 0] = i0; S.impr[q * 2 + 1] = i1;
     // :620-637 wipeout of species[1]
     uint32_t rng = S.rng[q];
-    double u = fast_random_at(S, step, S.memetic ? 2 : 0);
+    double u = fast_random_at(S, stream_step(S, q, step), S.memetic ? 2 : 0);
     if(u < 0.1 || !i1)
     {
         for(int i = 0; i < n; i++)

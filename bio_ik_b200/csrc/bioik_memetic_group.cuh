@@ -231,7 +231,7 @@ template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOI
     __syncwarp();
 
     double dp = 0.0000001;                                                                                // :450
-    if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
+    if(S.uniform[(6165936u + (uint32_t)stream_step(S, q, step) * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
     const bool quad = S.memetic == 'q';
 
     // component c (= 7 t + k) of the full approximation of a genotype x given as dx = x - base per pair: the FMA chain of

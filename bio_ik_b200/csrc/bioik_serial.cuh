@@ -292,7 +292,7 @@ template <int BS, bool DS, bool FS> __device__ __forceinline__ void serial_tasks
     if(do_memetic)
     {
         double dp = 0.0000001;                                                                                // :450
-        if(S.uniform[(6165936u + (uint32_t)step * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
+        if(S.uniform[(6165936u + (uint32_t)stream_step(S, q, step) * 3u + (uint32_t)slot) & ((1u << 23) - 1)] < 0.5) dp = -dp; // :451 fast_random()
         const bool quad = S.memetic == 'q';
         // Fast path for the plugin's default problem (exactly one primary PoseGoal, one tip): tip frames and goal
         // parameters stay in registers; the Pose goal does not read the genes, so the n one-variable evaluations
@@ -504,7 +504,7 @@ template <int BS, bool DS, bool FS> __device__ __forceinline__ void serial_tasks
             {
                 // :620-637 wipeout of species[1]; then the random_index draws of the next step's generations (:369)
                 uint32_t rng = S.rng[q];
-                const double u = S.uniform[(6165936u + (uint32_t)step * (S.memetic ? 3u : 1u) + (S.memetic ? 2u : 0u)) & ((1u << 23) - 1)];
+                const double u = S.uniform[(6165936u + (uint32_t)stream_step(S, q, step) * (S.memetic ? 3u : 1u) + (S.memetic ? 2u : 0u)) & ((1u << 23) - 1)];
                 if(u < 0.1 || !improved)
                 {
                     for(int i = 0; i < n; i++)

@@ -21,7 +21,7 @@ class IKSolver:
     """One solver context on one GPU.  `population` is children.size() of the reference (2 parents +
     child_count, 18 in the reference; BASELINE "pop")."""
 
-    def __init__(self, robot_model, mode="bio2_memetic", population=18, generations=None, memetic_iters=8, random_seed=1, device=0, reference_stale_tips=False):
+    def __init__(self, robot_model, mode="bio2_memetic", population=18, generations=None, memetic_iters=8, random_seed=1, device=0, reference_stale_tips=False, island_stream_stride=0):
         if mode not in MODES:
             raise BioIKError(_abi.E_INVALID, f"class not found {mode}")  # IKFactory::create, src/utils.h:432-437
         self.lib = _abi.load_library()
@@ -39,6 +39,8 @@ class IKSolver:
             raise BioIKError(rc, self.lib.bioik_last_error(None).decode())
         if reference_stale_tips:
             self.set_option(_abi.OPT_REFERENCE_STALE_TIPS, 1)
+        if island_stream_stride:
+            self.set_option(_abi.OPT_ISLAND_STREAM_STRIDE, island_stream_stride)
 
     def cancel(self):
         """IKBase::canceled: stop the solve in flight (callable from another thread)"""

@@ -215,8 +215,14 @@ int bioik_solve_batch_trace(bioik_ctx* ctx, int32_t B, const double* goal_params
  *   phenotypes3[0] held before - the write of an earlier probe, or the frames of the last f3 evaluation (:494) of the previous
  *   iteration / species / step; a fresh reference solver reads uninitialised memory there, this library starts from
  *   identity frames.  With 0 the probe scores those tips on the unmoved frame (out[t] = in[t], the evident intent).
- *   Single-chain problems (every variable moves every tip) are unaffected. */
-enum { BIOIK_OPT_REFERENCE_STALE_TIPS = 1 };
+ *   Single-chain problems (every variable moves every tip) are unaffected.
+ * BIOIK_OPT_ISLAND_STREAM_STRIDE (default 0): the islands of a query (bioik_begin / bioik_solve_islands with islands > 1) are,
+ *   like IKParallel's threads (src/ik_parallel.h:84-86, src/utils.h:423: clones of one solver), replicas that replay
+ *   ONE sequence of gaussians / rate exponents / fast_random values and differ only through their minstd_rand seeds (wipe-out
+ *   re-rolls, pre-selection counts).  A value k > 0 starts island i `i * k` solver steps into that sequence, so the islands
+ *   mutate differently from their first generation; island 0 and every plain batch are unaffected.  Results are then not those of
+ *   the reference's clone islands (the oracle restates the option; tests/test_islands.py). */
+enum { BIOIK_OPT_REFERENCE_STALE_TIPS = 1, BIOIK_OPT_ISLAND_STREAM_STRIDE = 2 };
 int bioik_set_option(bioik_ctx* ctx, int32_t option, int32_t value);
 
 /* IKBase::canceled (src/ik_base.h:143; set for every solver when the driver finishes or times out, polled in the solver's

@@ -307,6 +307,8 @@ struct Options
     bool libm_sincos = false; // use libm sin/cos instead of det_sincos (deviation study only)
     bool fma_approx = true;   // FMA in the approximator like the reference's AVX path; false = scalar path (:1174-1233)
     bool fma_approx1 = true;  // same switch for computeApproximateMutation1 alone (experiments)
+    int island_stride = 0;    // BIOIK_OPT_ISLAND_STREAM_STRIDE of the product (not a reference feature): island i of solveIslands starts
+                              // i * island_stride solver steps into the query-independent random streams
     bool stale_tips = false;  // emulate quirk Q2 of the reference (forward_kinematics.h:940): tips a variable does not move keep
                               // whatever the output buffer held before (pinning study only; never set on the parity path)
 };
@@ -1720,6 +1722,18 @@ inline IslandRuns solveIslands(const RobotModel& robot, const Tables& tables, co
     {
         solvers.emplace_back(new IKEvolution2(&robot, tables, rng_seeds[i], cfg, opt));
         solvers.back()->initialize(problem);
+        if(opt.island_stride > 0 && i > 0)
+        {
+            // The cursors of the table-driven streams (XORShift64 state, fast_random index, gaussian index) advance by the same
+            // amounts for every query and seed, so a throw-away clone that takes i * stride steps holds exactly the cursors
+            // island i starts from; its minstd_rand stays the freshly seeded one.
+            IKEvolution2 ahead(&robot, tables, rng_seeds[i], cfg, opt);
+            ahead.initialize(problem);
+            for(size_t k = 0; k < i * (size_t)opt.island_stride; k++) ahead.step();
+            solvers.back()->_xorshift = ahead._xorshift;
+            solvers.back()->random_buffer_index = ahead.random_buffer_index;
+            solvers.back()->random_gauss_index = ahead.random_gauss_index;
+        }
     }
     IslandRuns r;
     r.solutions.resize(islands), r.fitness.assign(islands, 0.0), r.success.assign(islands, 0), r.steps.assign(islands, 0);

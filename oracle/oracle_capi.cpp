@@ -461,6 +461,7 @@ int oracle_solve_islands(const BioikRobot* robot, const BioikProblem* problem, c
         opt.fma_approx = (flags & 2) == 0;
         opt.fma_approx1 = (flags & 4) == 0;
         opt.stale_tips = (flags & 8) != 0;
+        opt.island_stride = (flags >> 8) & 0xff; // bits 8..15: BIOIK_OPT_ISLAND_STREAM_STRIDE
         const Tables& tb = *(const Tables*)tables;
         std::atomic<int> failed(0);
         std::string err;

@@ -1,5 +1,6 @@
 """Latency of ONE MoveIt-style query answered by many islands (bioik_solve_islands): host buffers in, wrapped solution
-out, early exit at the driver's 4-step checks.  usage: python profiles/single_query_latency.py [population]"""
+out, early exit at the driver's 4-step checks - with the islands as clones of one random stream (the reference's threads) and with
+BIOIK_OPT_ISLAND_STREAM_STRIDE = 1.  usage: python profiles/single_query_latency.py [population]"""
 import os
 import sys
 import time
@@ -12,10 +13,12 @@ from bio_ik_b200.solver import IKSolver
 
 pop = int(sys.argv[1]) if len(sys.argv) > 1 else 18
 w = workloads.cfg2(256)
+from bio_ik_b200 import _abi
 solver = IKSolver(w.robot, mode="bio2_memetic", population=pop, random_seed=1, device=0).initialize(w.problem)
 w.generate(lambda rm, pr, v: solver.fk(v), B=256, cfg_id=2)
-for islands in (1, 16, 64, 256, 1024):
-    for steps in (8, 25):
+for stride, islands in [(0, 1), (0, 16), (1, 16), (0, 64), (1, 64), (0, 256), (1, 256)]:
+    solver.set_option(_abi.OPT_ISLAND_STREAM_STRIDE, stride)
+    for steps in (4, 8, 25):
         lat, ok = [], []
         for q in range(64):
             gp, sd = w.goal_params[q:q + 1], w.seeds[q:q + 1]
@@ -26,4 +29,4 @@ for islands in (1, 16, 64, 256, 1024):
             lat.append(time.perf_counter() - t0)
             ok.append(int(r["success"][0]))
         lat = np.array(lat) * 1e3
-        print(f"pop {pop} islands {islands:5d} step budget {steps:2d}: median {np.median(lat):.2f} ms  p90 {np.percentile(lat, 90):.2f} ms  success {np.mean(ok):.2f}")
+        print(f"pop {pop} stream stride {stride} islands {islands:5d} step budget {steps:2d}: median {np.median(lat):.2f} ms  p90 {np.percentile(lat, 90):.2f} ms  success {np.mean(ok):.2f}")

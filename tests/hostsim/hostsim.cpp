@@ -218,8 +218,9 @@ static int g_stale = 0;
 void hostsim_set_stale_tips(int on) { g_stale = on; }
 
 // islands per query of the next hostsim_solve calls (0: plain batch), for early_exit == 2
-static int g_islands = 0;
+static int g_islands = 0, g_island_stride = 0;
 void hostsim_set_islands(int islands) { g_islands = islands; }
+void hostsim_set_island_stride(int stride) { g_island_stride = stride; } // BIOIK_OPT_ISLAND_STREAM_STRIDE
 
 // the launch sequence of enqueue_solve() in bioik_capi.cu, on host memory
 int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const BioikSolverCfg* cfg, int B, const double* goal_params, const double* seeds, const uint32_t* rng_seeds, int steps, int early_exit, double* out_solutions,
@@ -233,7 +234,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     if(rc) return rc;
     std::vector<int32_t> go;
     std::vector<uint8_t> re;
-    make_schedules(std::max(steps, 1), cfg->generations, cfg->population, P.n, go, re);
+    make_schedules(std::max(steps, 1) + (g_islands > 1 ? (g_islands - 1) * g_island_stride : 0), cfg->generations, cfg->population, P.n, go, re);
     size_t n = P.n, T = P.T, gens = cfg->generations;
     std::vector<double> genes(B * 4 * n), grads(B * 4 * n), sfit(B * 2), sol(B * n), solfit(B), base(B * 2 * n), tip0(B * 2 * T * 7), delta(B * 2 * T * n * 7);
     std::vector<int32_t> impr(B * 2), done(B), stp(B), succ(B), cc(B * 2 * gens), qstep(B);
@@ -250,7 +251,7 @@ int hostsim_solve(const BioikRobot* robot, const BioikProblem* problem, const Bi
     }
     DState S;
     memset(&S, 0, sizeof(S));
-    S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit, S.islands = g_islands;
+    S.B = B, S.C = cfg->population, S.gens = cfg->generations, S.memetic = cfg->memetic, S.memetic_iters = cfg->memetic_iters, S.total_steps = steps, S.early_exit = early_exit, S.islands = g_islands, S.island_stride = g_islands > 1 ? g_island_stride : 0;
     S.goal_params = goal_params, S.seeds = seeds, S.rng_seeds = rng_seeds;
     S.genes = genes.data(), S.grads = grads.data(), S.sfit = sfit.data(), S.impr = impr.data(), S.sol = sol.data(), S.solfit = solfit.data(), S.rng = rng.data(), S.done = done.data(), S.steps = stp.data(),
     S.success = succ.data(), S.ccount = cc.data(), S.qstep = qstep.data(), S.carry = carry.data(), S.cancel = nullptr, S.base = base.data(), S.tip0 = tip0.data(), S.delta = delta.data();

@@ -30,8 +30,9 @@ class HostSim:
         if rc != 0:
             raise RuntimeError(f"hostsim rc={rc}: " + self.lib.hostsim_last_error().decode())
 
-    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, fast=False, islands=0, evolve_lanes=16, stale_tips=False):
+    def solve(self, robot, problem, cfg, goal_params, seeds, rng_seeds, steps, early_exit=False, fast=False, islands=0, evolve_lanes=16, stale_tips=False, island_stride=0):
         self.lib.hostsim_set_islands(int(islands))
+        self.lib.hostsim_set_island_stride(int(island_stride))
         self.lib.hostsim_set_stale_tips(int(stale_tips))
         self.lib.hostsim_set_evolve_lanes(int(evolve_lanes))
         seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)

@@ -140,7 +140,7 @@ class Oracle:
         return res
 
 
-def oracle_solve_islands(o, robot, problem, cfg, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=0, wrap=True, flags=0, nthreads=0):
+def oracle_solve_islands(o, robot, problem, cfg, goal_params, seeds, islands, steps, rng_seeds=None, early_exit=0, wrap=True, flags=0, nthreads=0, island_stride=0):
     """the oracle's statement of bioik_solve_islands (lock-step islands, IKParallel's selection, the plugin's wrap);
     early_exit: 0 none, 1 per island, 2 per query (the reference's `finished` flag).  res["runs"] holds the per-island results."""
     seeds = np.ascontiguousarray(seeds, dtype=np.float64).reshape(-1, robot.n_vars)
@@ -152,6 +152,7 @@ def oracle_solve_islands(o, robot, problem, cfg, goal_params, seeds, islands, st
     runs = dict(solutions=np.zeros((B, robot.n_vars)), fitness=np.zeros(B), success=np.zeros(B, dtype=np.int32), steps=np.zeros(B, dtype=np.int32))
     r, p = robot.to_abi(), problem.to_abi()
     nthreads = nthreads or min(Q, os.cpu_count() or 1)
+    flags = int(flags) | (int(island_stride) << 8)  # bits 8..15: the product's BIOIK_OPT_ISLAND_STREAM_STRIDE
     o._check(o.lib.oracle_solve_islands(C.byref(r), C.byref(p), C.byref(cfg), o.tables(cfg.table_seed), Q, islands, _abi.dptr(gp), _abi.dptr(seeds), _abi.uptr(rs), steps, int(early_exit), int(wrap), flags, nthreads,
                                         _abi.dptr(res["solutions"]), _abi.dptr(res["fitness"]), _abi.iptr(res["success"]), _abi.iptr(res["island"]), _abi.iptr(res["steps"]),
                                         _abi.dptr(runs["solutions"]), _abi.dptr(runs["fitness"]), _abi.iptr(runs["success"]), _abi.iptr(runs["steps"])))

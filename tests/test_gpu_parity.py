@@ -351,6 +351,28 @@ def test_solve_islands_matches_the_oracle(oracle, name, Q, islands, steps, early
     assert np.array_equal(a["solutions"], b["solutions"])
 
 
+@pytest.mark.parametrize("name,Q,islands,steps,early,stride", [("cfg2", 16, 8, 12, 0, 1), ("cfg2", 12, 6, 25, 2, 2), ("cfg4", 6, 4, 8, 2, 1), ("cfg3", 8, 3, 6, 0, 1)])
+def test_island_stream_stride_matches_the_oracle(oracle, name, Q, islands, steps, early, stride):
+    """BIOIK_OPT_ISLAND_STREAM_STRIDE: island i starts i * stride steps into the shared random streams (the oracle restates the option)"""
+    w = workloads.make(name, ofk(oracle), batch=Q)
+    solver = IKSolver(w.robot, mode="bio2_memetic", population=40, random_seed=1, device=0, island_stream_stride=stride).initialize(w.problem)
+    cfg = oracle_lib.make_cfg(population=40)
+    got = solver.solve_islands(w.goal_params, w.seeds, islands, steps, early_exit=early)
+    ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=early, island_stride=stride)
+    for k in ("solutions", "fitness", "success", "island", "steps"):
+        assert np.array_equal(got[k], ref[k]), k
+    # a plain batch on the same context is not affected by the option
+    a = solver.solve_batch(w.goal_params, w.seeds, w.rng_seeds, 3)
+    b = oracle.solve(w.robot, w.problem, cfg, w.goal_params, w.seeds, w.rng_seeds, 3)
+    assert np.array_equal(a["solutions"], b["solutions"])
+    # and switching it off gives the clone islands back
+    solver.set_option(_abi.OPT_ISLAND_STREAM_STRIDE, 0)
+    got = solver.solve_islands(w.goal_params, w.seeds, islands, steps, early_exit=early)
+    ref = oracle_lib.oracle_solve_islands(oracle, w.robot, w.problem, cfg, w.goal_params, w.seeds, islands, steps, early_exit=early)
+    for k in ("solutions", "fitness", "success", "island", "steps"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
 def test_solve_islands_default_goal_parameters_and_seeds(oracle):
     rm, groups = robots.pr2_like()
     g = groups["right_arm"]
