@@ -408,7 +408,9 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     const unsigned smask = (LPT == 32 || LPT == 16) ? 0xffffffffu : gmask;
     if(task >= S.B * 2) return;
     const int q = task >> 1, slot = task & 1;
-    if(run_done(S, q, step)) return;
+    // asked first, acted on after the staging loads below are in flight: the flags it reads are another round trip to L2
+    const bool finished = run_done(S, q, step);
+    const bool has_sec = LEAN ? false : P.has_secondary != 0; // (a single primary PoseGoal has no secondary goals: compile-time for the LEAN forms)
     const int n = NG ? NG : P.n, C = S.C, G = P.G;
     const int R = mtab_row(C);
     const int nchunks = R / (LPT * CH); // R is a power of two >= LPT * CH (select_evolve_fast)
@@ -427,7 +429,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 nj++;
             }
 
-    FastSmem L{n, TM ? P.T : T, G, JOINT ? P.n_joint_goals : 0, P.has_secondary ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
+    FastSmem L{n, TM ? P.T : T, G, JOINT ? P.n_joint_goals : 0, has_sec ? 0 : 1, TM ? P.tip_gene_start[P.T] : 0};
     const int TT = TM ? P.T : T; // tips of the problem
     double *s_rec = W + L.off_rec(), *s_term = W + L.off_term(), *s_delta = W + L.off_delta(), *s_par = W + L.off_par(), *s_pg = W + L.off_pg();
     double *s_tip0 = W + L.off_tip0(), *s_gp = W + L.off_gp(), *s_jrec = W + L.off_jrec(), *s_jq = W + L.off_jq(), *s_fit = W + L.off_fit(), *s_sf = W + L.off_sf();
@@ -473,6 +475,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
         }
     }
     for(int k = lane; k < G * GOAL_NPARAM; k += LPT) s_gp[k] = S.goal_params[(size_t)q * G * GOAL_NPARAM + k];
+    if(finished) return; // the run is over (all lanes of the task - with 16 lanes per task: of the warp - agree); nothing was written
     __syncwarp(smask);
     if(TM) // the per-task part of the pair records: base and clip limits of the pair's gene
         for(int idx = lane; idx < L.pairs; idx += LPT)
@@ -520,6 +523,9 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     if(lane < 2) pf = TM ? fast_eval_one_tips<JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed) : fast_eval_one<T, GSPEC, JOINT>(P, n, s_par + lane * n, s_rec, s_delta, s_tip0, s_gp, s_jrec, seed);
     double f_par0 = __shfl_sync(smask, pf, lane0 + 0), f_par1 = __shfl_sync(smask, pf, lane0 + 1);
 
+    // clamp elision (below): the largest mutation of this lane's gene, hoisted out of the generation loop
+    double lean_reach = 0.0;
+    if(LEAN && lane < n) lean_reach = S.gauss_absmax * (1.0 / 256.0) * P.genes[lane].span;
     int cur = 0;                 // parent buffer in use
     const int parity = lane & 1; // child slot c = j + 2 is even <=> lane is even
     // EARLY: the first mutation-table row of a chunk is requested while the previous chunk's fitness (or the previous generation's
@@ -538,7 +544,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
     {
         const int call = (stream_step(S, q, step) * 2 + slot) * S.gens + gen;
         const double* mt = mtab + (size_t)call * n * R;
-        const int child_count = P.has_secondary ? S.ccount[((size_t)q * 2 + slot) * S.gens + gen] : C;
+        const int child_count = has_sec ? S.ccount[((size_t)q * 2 + slot) * S.gens + gen] : C;
         double* par = s_par + cur * 4 * n;
         const double *p_g0 = par, *p_g1 = par + n, *p_gr0 = par + 2 * n, *p_gr1 = par + 3 * n;
 
@@ -564,7 +570,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 // (mutation_rate <= 2^15 / 2^23, :265,:290-293) and t in {0, pg, 2 pg} (:294-296).  If g0 keeps that distance (plus
                 // rounding slack) from both clip limits, clamp() returns its argument for all children and is skipped for the gene.
                 const double g0 = p_g0[i];
-                const double e = (S.gauss_absmax * (1.0 / 256.0) * P.genes[i].span + 2.0 * BIOIK_FMAX(BIOIK_FABS(pge), BIOIK_FABS(pgo))) * 1.000001;
+                const double e = (lean_reach + 2.0 * BIOIK_FMAX(BIOIK_FABS(pge), BIOIK_FABS(pgo))) * 1.000001; // i == lane: n <= 8 < LPT
                 const double slack = e + 1e-15 * (BIOIK_FABS(g0) + e);
 #ifndef BIOIK_X_NOELIDE
                 gene_safe = (g0 - slack > s_rec[4 * i + 2]) && (g0 + slack < s_rec[4 * i + 3]); // false for NaN: the clamp stays
@@ -920,7 +926,7 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                             prim += v * gl.weight_sq;
                     }
                 }
-                if(P.has_secondary)
+                if(has_sec)
                 {
                     if(c < C)
                     {
@@ -947,13 +953,13 @@ __device__ __forceinline__ void evolve_fast_task(const DProblem& P, const DState
                 }
             }
         }
-        if(!P.has_secondary && !LEAN)
+        if(!has_sec && !LEAN)
         {
             k1 = q1 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b1);
             k2 = q2 == 0xFFFFFFFFu ? FAST_KEY_NONE : fast_fitness_key(b2);
         }
 
-        if(P.has_secondary)
+        if(has_sec)
         {
             // pre-selection (:366-378): position = 2 + stable rank of the secondary fitness; only the first
             // child_count positions take part in the selection
