@@ -111,10 +111,12 @@ inline int memetic_group_width(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : 32);
 // is what the harness of the reference build pre-fills - a fresh reference solver reads uninitialised memory there).
 // blocks per SM the register allocation aims for: the kernel is a chain of short dependent phases (latency-bound), so more
 // resident warps beat a larger register file per thread (80 registers, no spills; measured: profiles/r02_experiments.md)
+// (the 16-lane form - two tasks per warp, problems of 9 ... 16 variables - is the exception: four blocks with 128 registers run cfg3's
+// memetic phase in 4.5 ms per pass against 4.75 ms at six; the 32-lane form loses 10 % that way)
 #ifndef BIOIK_MG_MINBLOCKS
 #define BIOIK_MG_MINBLOCKS 6
 #endif
-template <int W, bool STALE = false> __global__ void __launch_bounds__(128, BIOIK_MG_MINBLOCKS) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
+template <int W, bool STALE = false> __global__ void __launch_bounds__(128, (W == 16 ? 4 : BIOIK_MG_MINBLOCKS)) k_memetic_group(BIOIK_PROBLEM_PARAM, DState S, int step)
 {
     extern __shared__ double smem[];
     constexpr int GPW = 32 / W;
