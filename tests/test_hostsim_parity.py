@@ -285,7 +285,7 @@ def test_virtual_joints_that_mimic(sim, oracle):
             assert np.array_equal(a[k], b[k]), (k, fast)
 
 
-@pytest.mark.parametrize("B,pop,mode,steps,early", [(5, 128, "q", 5, False), (19, 64, "q", 3, False), (33, 128, "l", 2, False), (18, 64, "q", 9, True), (3, 200, 0, 3, False)])
+@pytest.mark.parametrize("B,pop,mode,steps,early", [(5, 128, "q", 5, False), (19, 64, "q", 3, False), (33, 128, "l", 2, False), (18, 128, "q", 9, True), (3, 200, 0, 3, False)])
 def test_persistent_kernel_is_bit_identical_to_the_oracle(sim, oracle, B, pop, mode, steps, early):
     """bioik_persist.cuh: the whole solve as work items (evolve(query, step), serial(group of 16 queries, step)) taken from two
     queues by resident warps - here by ONE simulated warp, in two launches with a cut in the middle (the resume path of
